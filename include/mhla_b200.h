@@ -1,0 +1,132 @@
+/*
+ * mhla_b200 -- C ABI of the B200-native MHLA forward operator (sm_100a).
+ *
+ * The reference (DAGroup-PKU/MHLA) is pure Python and has no FFI / plugin interface for this path
+ * (SURVEY.md 8b): the operator is inline PyTorch in
+ *   - mhla_dit/mhla/mhla.py:262-268                              (variant A, block-mixed + normaliser)
+ *   - mhla_image_classification/models/modules/attention/mhla.py:275-282   (twin of A)
+ *   - mhla_videogen/diffusion/model/wan/mhla_utils.py:328-341    (variant B, roped numerator)
+ *   - mhla_nlp/fla/ops/mhla/naive.py:10-83, :88-142              (variant C, causal chunked / recurrent)
+ * This header therefore DEFINES the boundary a binding would use; each entry point cites the reference
+ * lines it replaces.  INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only (no torch types); all pointers are DEVICE pointers unless
+ * stated; the caller owns inputs, outputs and workspace; calls only enqueue work on `stream` (a
+ * cudaStream_t passed as void*) -- they never allocate device memory and never synchronise the device.
+ * Return value: 0 on success, a negative mhla_status otherwise (see mhla_strerror).  Thread-safe and
+ * re-entrant across streams (the only process-wide state is a mutex-guarded tensor-map cache).
+ */
+#ifndef MHLA_B200_H_
+#define MHLA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MHLA_B200_ABI_VERSION 1
+
+typedef enum mhla_status {
+  MHLA_OK = 0,
+  MHLA_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, bad dtype / flag */
+  MHLA_ERR_UNSUPPORTED_SHAPE = -2, /* shape outside the kernel's envelope (see each entry point) */
+  MHLA_ERR_ALIGNMENT = -3,        /* pointer not 16-byte aligned or stride not a multiple of 8 elements */
+  MHLA_ERR_WORKSPACE = -4,        /* workspace NULL or smaller than mhla_*_workspace_bytes() */
+  MHLA_ERR_CUDA = -5,             /* a CUDA runtime/driver call failed (see mhla_last_cuda_error) */
+  MHLA_ERR_NO_DEVICE = -6         /* current device is not sm_100 */
+} mhla_status;
+
+typedef enum mhla_dtype { MHLA_BF16 = 0, MHLA_FP16 = 1 } mhla_dtype;
+
+enum {
+  MHLA_FLAG_NORMALIZE = 1 << 0, /* divide by the (quirky) block-mixed normaliser, mhla.py:265-268 */
+  MHLA_FLAG_UNFUSED = 1 << 8,   /* debugging: run the three phases as separate launches */
+  MHLA_FLAG_STOP_AFTER_P1 = 1 << 9,  /* debugging (with UNFUSED): stop after the block summaries */
+  MHLA_FLAG_STOP_AFTER_P2 = 1 << 10  /* debugging (with UNFUSED): stop after the block mixing */
+};
+
+/*
+ * A strided view of a [B, H, M, w, D] tensor (batch, head, block, token-in-block, channel).
+ * Strides are in ELEMENTS; the channel stride is 1.  This covers the reference's block-major
+ * "(b h) n w d" layout (mhla.py:232-236) as well as token-major [B, N, H, D] tensors whose blocks
+ * are contiguous token ranges.
+ */
+typedef struct mhla_tensor5 {
+  const void* ptr;
+  int64_t stride_b, stride_h, stride_m, stride_w;
+} mhla_tensor5;
+
+/*
+ * Non-causal block-mixed forward (variants A and B):
+ *   S_j   = Kn_j^T V_j                              (mhla.py:262 / mhla_utils.py:331)
+ *   S~_i  = sum_j mix[i, j] S_j                     (mhla.py:263 / mhla_utils.py:332; the 1x1 Conv2d)
+ *   den_i[t] = sum_j mix[i, j] (q_{j,t} . sum_s k_{j,s}) + eps     (mhla.py:265-266, the reference's quirk)
+ *   out_i = (Qn_i S~_i) / den_i                     (mhla.py:268 / mhla_utils.py:339-341)
+ * where Qn/Kn are q_rope/k_rope when given (variant B) and q/k otherwise, while the normaliser always
+ * uses the un-roped q/k (mhla_utils.py:334-338).
+ * Envelope: D in {64, 128} (Dk == Dv); 1 <= w <= 256; M >= 1; bf16 or fp16 I/O, fp32 accumulation,
+ * TF32 block mixing; mix is fp32 [M, M] row-major with leading dimension mix_ld (elements).
+ */
+typedef struct mhla_blockmix_desc {
+  int32_t B, H, M, w, D;
+  int32_t dtype;         /* mhla_dtype */
+  uint32_t flags;        /* MHLA_FLAG_* */
+  float eps;
+  mhla_tensor5 q, k, v;  /* q,k: un-roped (used by the normaliser; also the numerator if *_rope are NULL) */
+  mhla_tensor5 q_rope, k_rope; /* ptr == NULL when absent */
+  mhla_tensor5 out;      /* written; same dtype as the inputs */
+  const float* mix;      /* [M, M] fp32, y_i = sum_j mix[i*mix_ld + j] x_j */
+  int64_t mix_ld;
+  void* workspace;       /* >= mhla_blockmix_workspace_bytes(desc) bytes, 1024-byte aligned */
+  size_t workspace_bytes;
+} mhla_blockmix_desc;
+
+size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);
+/* White-box view of the workspace for tests: out[0..7] = byte offsets of S, S~, den, padded mix, counters,
+ * then ncols (floats per S row: D*D summaries followed by wpad n_loc entries), wpad, padded mix pitch. */
+int mhla_blockmix_workspace_layout(const mhla_blockmix_desc* desc, size_t out[8]);
+int mhla_fwd_blockmix(const mhla_blockmix_desc* desc, void* stream);
+
+/*
+ * Causal chunked forward (variant C), replaces naive_chunk_simple_mhla_fixed
+ * (mhla_nlp/fla/ops/mhla/naive.py:10-83) and, for T <= chunk, naive_recurrent_mhla (:88-142):
+ *   o = K^-1/2 ((Q K^T) * Mask) V,  Mask[t, s] = mm[t / chunk, s / chunk] * 1[s <= t]
+ * q,k: [B, T, H, K], v,o: [B, T, H, V] with element strides (stride_b, stride_t, stride_h, 1);
+ * T is zero-padded to a multiple of `chunk` (naive.py:46-51); mm is fp32 [L, L] row-major, L >= ceil(T/chunk).
+ * Envelope: chunk == 64; K in {64, 128}; V in {64, 128, 256}.
+ */
+typedef struct mhla_tensor4 {
+  const void* ptr;
+  int64_t stride_b, stride_t, stride_h;
+} mhla_tensor4;
+
+typedef struct mhla_causal_desc {
+  int32_t B, T, H, K, V;
+  int32_t chunk;
+  int32_t dtype;
+  uint32_t flags;
+  float scale;           /* K^-1/2 in the reference (naive.py:42) */
+  mhla_tensor4 q, k, v, out;
+  const float* mm;       /* [L, L] fp32 */
+  int64_t mm_ld;
+  int32_t L;
+  void* workspace;
+  size_t workspace_bytes;
+} mhla_causal_desc;
+
+size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc);
+int mhla_fwd_causal(const mhla_causal_desc* desc, void* stream);
+
+/* Misc. */
+int mhla_abi_version(void);
+const char* mhla_strerror(int status);
+const char* mhla_last_cuda_error(void);   /* thread-local text of the last CUDA failure, "" if none */
+/* Number of kernel launches (memsets excluded) the last successful mhla_fwd_* call on this thread made. */
+int mhla_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MHLA_B200_H_ */

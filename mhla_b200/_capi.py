@@ -1,0 +1,93 @@
+"""ctypes binding of libmhla_b200.so (see include/mhla_b200.h).  No CPU fallback: if the library is missing
+or a call fails the caller gets an exception."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmhla_b200.so")
+
+MHLA_BF16, MHLA_FP16 = 0, 1
+FLAG_NORMALIZE = 1 << 0
+FLAG_UNFUSED = 1 << 8
+FLAG_STOP_AFTER_P1 = 1 << 9
+FLAG_STOP_AFTER_P2 = 1 << 10
+
+EXPORTS = [
+    "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
+]
+
+
+class Tensor5(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride_b", C.c_int64), ("stride_h", C.c_int64), ("stride_m", C.c_int64),
+                ("stride_w", C.c_int64)]
+
+
+class BlockmixDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("H", C.c_int32), ("M", C.c_int32), ("w", C.c_int32), ("D", C.c_int32),
+        ("dtype", C.c_int32), ("flags", C.c_uint32), ("eps", C.c_float),
+        ("q", Tensor5), ("k", Tensor5), ("v", Tensor5), ("q_rope", Tensor5), ("k_rope", Tensor5), ("out", Tensor5),
+        ("mix", C.c_void_p), ("mix_ld", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class Tensor4(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("stride_b", C.c_int64), ("stride_t", C.c_int64), ("stride_h", C.c_int64)]
+
+
+class CausalDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("T", C.c_int32), ("H", C.c_int32), ("K", C.c_int32), ("V", C.c_int32),
+        ("chunk", C.c_int32), ("dtype", C.c_int32), ("flags", C.c_uint32), ("scale", C.c_float),
+        ("q", Tensor4), ("k", Tensor4), ("v", Tensor4), ("out", Tensor4),
+        ("mm", C.c_void_p), ("mm_ld", C.c_int64), ("L", C.c_int32),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class MhlaError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load the extension (once).  Raises ImportError when it has not been built - there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m mhla_b200.build` (nvcc, sm_100a). "
+                "mhla_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.mhla_abi_version.restype = C.c_int
+        L.mhla_strerror.restype = C.c_char_p
+        L.mhla_strerror.argtypes = [C.c_int]
+        L.mhla_last_cuda_error.restype = C.c_char_p
+        L.mhla_last_launch_count.restype = C.c_int
+        L.mhla_blockmix_workspace_bytes.restype = C.c_size_t
+        L.mhla_blockmix_workspace_bytes.argtypes = [C.POINTER(BlockmixDesc)]
+        L.mhla_blockmix_workspace_layout.restype = C.c_int
+        L.mhla_blockmix_workspace_layout.argtypes = [C.POINTER(BlockmixDesc), C.POINTER(C.c_size_t * 8)]
+        L.mhla_fwd_blockmix.restype = C.c_int
+        L.mhla_fwd_blockmix.argtypes = [C.POINTER(BlockmixDesc), C.c_void_p]
+        L.mhla_causal_workspace_bytes.restype = C.c_size_t
+        L.mhla_causal_workspace_bytes.argtypes = [C.POINTER(CausalDesc)]
+        L.mhla_fwd_causal.restype = C.c_int
+        L.mhla_fwd_causal.argtypes = [C.POINTER(CausalDesc), C.c_void_p]
+        if L.mhla_abi_version() != 1:
+            raise ImportError("libmhla_b200.so ABI version mismatch; rebuild with `python -m mhla_b200.build --force`")
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        L = lib()
+        msg = L.mhla_strerror(status).decode()
+        detail = L.mhla_last_cuda_error().decode()
+        raise MhlaError(f"{what} failed: {msg} ({status})" + (f" -- {detail}" if detail else ""))

@@ -1,0 +1,638 @@
+// Non-causal block-mixed MHLA forward (variants A/B) as ONE persistent, warp-specialised sm_100a kernel.
+//
+// Replaces the inline PyTorch operator of the reference:
+//   mhla_dit/mhla/mhla.py:262-268 and mhla_videogen/diffusion/model/wan/mhla_utils.py:328-341.
+//
+// Work is cut into three kinds of items that flow through one TMA->smem ring, one tcgen05 issuer and one
+// epilogue warpgroup (see DESIGN.md "Kernel"):
+//   P1 (g, j)        S_j = K_j^T V_j  (+ ksum_j via an all-ones B operand, n_loc[j,t] = q_{j,t}.ksum_j)
+//   P2 (g, it, ic)   [S~ | den] rows it*128.., cols ic*128.. = mix . [S | n_loc]    (TF32 GEMM over blocks)
+//   P3 (g, i)        O_i = (Q_i S~_i) / den_i
+// Items of different (b,h) groups g are interleaved in a fixed global order (P1(s), P3(s-lag3), P2(s-lag2))
+// so that the S / S~ / den workspace and the second read of Q are served from L2; cross-CTA dependencies
+// are per-group arrival counters in global memory (release/acquire), all CTAs are co-resident.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace mhla {
+
+constexpr int kStageBytes = 32768;
+constexpr int kNumStages = 6;
+constexpr int kStagingBytes = 16384;  // x2 (double buffered epilogue staging, [128 rows][128 B] swizzle-128B)
+constexpr int kThreads = 256;         // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: epilogue
+constexpr int kEpiThreads = 128;
+constexpr int kTmemCols = 512;
+constexpr int kAccCols = 256;         // two accumulator buffers of 256 columns
+constexpr int kKsumCol = 128;         // ksum accumulator columns [128,144) inside a P1 buffer
+
+constexpr int kSmemRing = 0;
+constexpr int kSmemStaging = kStageBytes * kNumStages;
+constexpr int kSmemOnes = kSmemStaging + 2 * kStagingBytes;
+constexpr int kSmemKsum = kSmemOnes + 512;
+constexpr int kSmemBars = kSmemKsum + 512;
+constexpr int kSmemTotal = kSmemBars + 256;
+constexpr int kSmemAlloc = kSmemTotal + 1024;  // slack for manual 1024-byte alignment
+
+struct alignas(64) BlockmixParams {
+  CUtensorMap tmK, tmV, tmKn, tmQn, tmQr;   // rank-5 (d, w, M, H, B) views; Kn/Qn: un-roped (normaliser)
+  CUtensorMap tmSst;                        // S store   : (Dv, Dk, G*M)      fp32, box (32, Dk, 1)
+  CUtensorMap tmSld;                        // S load    : (ncols, M, G)      fp32, box (32, 32, 1)
+  CUtensorMap tmW;                          // mix       : (Mp, M)            fp32, box (32, 128)
+  CUtensorMap tmStst;                       // S~ store  : (D*D, M, G)        bf16/fp16, box (64, 128, 1)
+  CUtensorMap tmDen;                        // den store : (wpad, M, G)       fp32, box (32, 128, 1)
+  CUtensorMap tmStld;                       // S~ load   : (Dv, Dk, G*M)      bf16/fp16, box (64, Dk, 1)
+  CUtensorMap tmO;                          // out       : rank-5 like q
+  float* ws_S;                              // [G*M][ncols] fp32: S_j (Dk*Dv) | n_loc_j (wpad)
+  const float* den;                         // [G*M][wpad]
+  uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
+  int G, H, M, w, TW, nsub;
+  int ncols, wpad;
+  int n2_rows, n2_cols, n2_scols;           // P2 tile grid; first n2_scols column tiles are S columns
+  int kslabs;                               // ceil(M / 32)
+  int normalize, ropenorm, is_fp16;
+  int mode;                                 // 0: fused; 1/2/3: only that phase (unfused debugging path)
+  int lag2, lag3;
+  float eps;
+};
+
+struct Item {
+  int type, g, t;
+};
+
+struct Sched {
+  int G, n1, n2, n3, lag2, lag3, mode, nsteps, stride;
+  int s;
+  long long off;
+  __device__ void init(const BlockmixParams& p) {
+    G = p.G; n1 = p.M; n2 = p.n2_rows * p.n2_cols; n3 = p.M;
+    lag2 = p.lag2; lag3 = p.lag3; mode = p.mode;
+    nsteps = G + (lag2 > lag3 ? lag2 : lag3);
+    stride = gridDim.x; s = 0; off = blockIdx.x;
+  }
+  __device__ bool next(Item& it) {
+    if (mode != 0) {
+      const int n = mode == 1 ? n1 : (mode == 2 ? n2 : n3);
+      if (off >= (long long)G * n) return false;
+      it.type = mode; it.g = (int)(off / n); it.t = (int)(off % n);
+      off += stride;
+      return true;
+    }
+    while (s < nsteps) {
+      const int c1 = (s < G) ? n1 : 0;
+      const int g3 = s - lag3, g2 = s - lag2;
+      const int c3 = (g3 >= 0 && g3 < G) ? n3 : 0;
+      const int c2 = (g2 >= 0 && g2 < G) ? n2 : 0;
+      const int tot = c1 + c3 + c2;
+      if (off >= tot) { off -= tot; ++s; continue; }
+      if (off < c1) { it.type = 1; it.g = s; it.t = (int)off; }
+      else if (off < c1 + c3) { it.type = 3; it.g = g3; it.t = (int)off - c1; }
+      else { it.type = 2; it.g = g2; it.t = (int)off - c1 - c3; }
+      off += stride;
+      return true;
+    }
+    return false;
+  }
+};
+
+struct Ring {
+  int stage = 0;
+  uint32_t phase = 0;
+  __device__ __forceinline__ void advance(int n = 1) {
+    stage += n;
+    while (stage >= kNumStages) { stage -= kNumStages; phase ^= 1; }
+  }
+  __device__ __forceinline__ Ring at(int k) const { Ring r = *this; r.advance(k); return r; }
+};
+
+__device__ __forceinline__ void spin_until(const uint32_t* cnt, uint32_t target) {
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(cnt) < target) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) { printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+}
+
+// Number of ring stages an item occupies (identical in every role).
+template <int D>
+__device__ __forceinline__ int p1_stages(const BlockmixParams& p) {
+  if constexpr (D == 64) return p.nsub * (1 + p.ropenorm) + p.normalize;
+  else return p.nsub * (2 + p.ropenorm) + p.normalize * p.nsub;
+}
+template <int D>
+__device__ __forceinline__ int p3_stages(const BlockmixParams& p) {
+  if constexpr (D == 64) return p.nsub;
+  else return 1 + p.nsub;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_constant__ BlockmixParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem + kSmemRing;
+  uint8_t* staging = smem + kSmemStaging;
+  uint16_t* ones = reinterpret_cast<uint16_t*>(smem + kSmemOnes);
+  float* ksum_s = reinterpret_cast<float*>(smem + kSmemKsum);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
+  uint64_t* empty = full + kNumStages;
+  uint64_t* tfull = empty + kNumStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tile_bytes = p.TW * 128;  // one [TW rows][64 x 16-bit] swizzle-128B tile
+  const uint32_t fmt16 = p.is_fp16 ? 0u : 1u;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kNumStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+    const CUtensorMap* maps = &p.tmK;
+    for (int i = 0; i < 12; ++i) tma_prefetch_desc(maps + i);
+  }
+  if (threadIdx.x < 256) ones[threadIdx.x] = p.is_fp16 ? 0x3C00 : 0x3F80;  // 1.0 in fp16 / bf16
+  if (warp == 2) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  fence_proxy_async_smem();  // the all-ones tile is read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  Sched sched; sched.init(p);
+  Item it;
+
+  if (warp == 0) {
+    // ============================================================ TMA producer (one lane)
+    if (lane == 0) {
+      Ring r;
+      while (sched.next(it)) {
+        const int b = it.g / p.H, h = it.g % p.H;
+        if (it.type == 1) {
+          const int j = it.t;
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            const int t0 = sub * p.TW;
+            if constexpr (D == 64) {
+              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              uint8_t* st = ring + r.stage * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
+              tma_load_5d(st, &p.tmK, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
+              tma_load_5d(st + 16384, &p.tmV, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
+              r.advance();
+            } else {
+              for (int kv = 0; kv < 2; ++kv) {
+                mbar_wait(&empty[r.stage], r.phase ^ 1);
+                uint8_t* st = ring + r.stage * kStageBytes;
+                mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
+                const CUtensorMap* tm = kv ? &p.tmV : &p.tmK;
+                tma_load_5d(st, tm, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
+                tma_load_5d(st + 16384, tm, &full[r.stage], 64, t0, j, h, b, kEvictFirst);
+                r.advance();
+              }
+            }
+            if (p.ropenorm) {
+              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              uint8_t* st = ring + r.stage * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.stage], (D / 64) * tile_bytes);
+              tma_load_5d(st, &p.tmKn, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
+              if constexpr (D == 128) tma_load_5d(st + 16384, &p.tmKn, &full[r.stage], 64, t0, j, h, b, kEvictFirst);
+              r.advance();
+            }
+          }
+          if (p.normalize) {
+            if constexpr (D == 64) {
+              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              uint8_t* st = ring + r.stage * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.stage], p.nsub * tile_bytes);
+              for (int sub = 0; sub < p.nsub; ++sub)
+                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.stage], 0, sub * p.TW, j, h, b, kEvictLast);
+              r.advance();
+            } else {
+              for (int sub = 0; sub < p.nsub; ++sub) {
+                mbar_wait(&empty[r.stage], r.phase ^ 1);
+                uint8_t* st = ring + r.stage * kStageBytes;
+                mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
+                tma_load_5d(st, &p.tmQn, &full[r.stage], 0, sub * p.TW, j, h, b, kEvictLast);
+                tma_load_5d(st + 16384, &p.tmQn, &full[r.stage], 64, sub * p.TW, j, h, b, kEvictLast);
+                r.advance();
+              }
+            }
+          }
+        } else if (it.type == 2) {
+          if (p.mode == 0) { spin_until(&p.counters[it.g], (uint32_t)p.M); fence_proxy_async_all(); }
+          const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+          for (int slab = 0; slab < p.kslabs; ++slab) {
+            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            uint8_t* st = ring + r.stage * kStageBytes;
+            mbar_arrive_expect_tx(&full[r.stage], 32768);
+            tma_load_2d(st, &p.tmW, &full[r.stage], slab * 32, ti * 128, kEvictLast);
+            for (int n4 = 0; n4 < 4; ++n4)
+              tma_load_3d(st + 16384 + n4 * 4096, &p.tmSld, &full[r.stage], tc * 128 + n4 * 32, slab * 32, it.g,
+                          kEvictNormal);
+            r.advance();
+          }
+        } else {
+          if (p.mode == 0) {
+            spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
+            fence_proxy_async_all();
+          }
+          const int i = it.t;
+          const CUtensorMap* tq = &p.tmQr;
+          if constexpr (D == 64) {
+            for (int sub = 0; sub < p.nsub; ++sub) {
+              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              uint8_t* st = ring + r.stage * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.stage], tile_bytes + (sub == 0 ? 8192 : 0));
+              tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
+              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.stage], 0, 0, it.g * p.M + i, kEvictFirst);
+              r.advance();
+            }
+          } else {
+            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            uint8_t* st = ring + r.stage * kStageBytes;
+            mbar_arrive_expect_tx(&full[r.stage], 32768);
+            tma_load_3d(st, &p.tmStld, &full[r.stage], 0, 0, it.g * p.M + i, kEvictFirst);
+            tma_load_3d(st + 16384, &p.tmStld, &full[r.stage], 64, 0, it.g * p.M + i, kEvictFirst);
+            r.advance();
+            for (int sub = 0; sub < p.nsub; ++sub) {
+              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              st = ring + r.stage * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
+              tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
+              tma_load_5d(st + 16384, tq, &full[r.stage], 64, sub * p.TW, i, h, b, kEvictFirst);
+              r.advance();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================================================ tcgen05 issuer (one lane)
+    if (lane == 0) {
+      Ring r;
+      uint32_t nitem = 0;
+      const uint32_t ring_addr = smem_u32(ring);
+      const uint32_t ones_addr = smem_u32(ones);
+      // all-ones B operand: no swizzle, MN-major, 2x2 core matrices of 128 B (LBO: K direction, SBO: N direction)
+      const uint64_t desc_ones = make_smem_desc(ones_addr, 256, 128, kSwizzleNone);
+      const uint32_t idesc_p1 = make_idesc(fmt16, 1, 1, D, D);
+      const uint32_t idesc_p1_ones = make_idesc(fmt16, 1, 1, D, 16);
+      const uint32_t idesc_p2 = make_idesc(2, 0, 1, 128, 128);
+      const uint32_t idesc_p3 = make_idesc(fmt16, 0, 1, 128, D);
+      while (sched.next(it)) {
+        const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
+        const uint32_t acc = tmem_base + ab * kAccCols;
+        mbar_wait(&tempty[ab], aphase ^ 1);
+        tc_fence_after();
+        if (it.type == 1) {
+          const int ksteps = p.TW / 16;
+          const bool ones_here = p.normalize && !p.ropenorm;
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            uint32_t a_addr, b_addr;
+            Ring r0 = r;
+            if constexpr (D == 64) {
+              mbar_wait(&full[r.stage], r.phase);
+              a_addr = ring_addr + r.stage * kStageBytes;
+              b_addr = a_addr + 16384;
+              r.advance();
+            } else {
+              mbar_wait(&full[r.stage], r.phase);
+              a_addr = ring_addr + r.stage * kStageBytes;
+              r.advance();
+              mbar_wait(&full[r.stage], r.phase);
+              b_addr = ring_addr + r.stage * kStageBytes;
+              r.advance();
+            }
+            tc_fence_after();
+            for (int ks = 0; ks < ksteps; ++ks) {
+              // MN-major, 128B swizzle: 8 token rows per atom (SBO = 1024 B), 64 channels per atom (LBO = 16 KB)
+              const uint64_t da = make_smem_desc(a_addr + ks * 2048, 16384, 1024, kSwizzle128);
+              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 16384, 1024, kSwizzle128);
+              mma_f16_ss(acc, da, db, idesc_p1, (sub | ks) != 0);
+              if (ones_here) mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
+            }
+            mma_commit(&empty[r0.stage]);
+            if constexpr (D == 128) mma_commit(&empty[r0.at(1).stage]);
+            if (p.ropenorm) {
+              mbar_wait(&full[r.stage], r.phase);
+              tc_fence_after();
+              const uint32_t n_addr = ring_addr + r.stage * kStageBytes;
+              for (int ks = 0; ks < ksteps; ++ks) {
+                const uint64_t da = make_smem_desc(n_addr + ks * 2048, 16384, 1024, kSwizzle128);
+                mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
+              }
+              mma_commit(&empty[r.stage]);
+              r.advance();
+            }
+          }
+          mma_commit(&tfull[ab]);
+          if (p.normalize) r.advance(D == 64 ? 1 : p.nsub);  // Q stages are consumed by the epilogue warps
+        } else if (it.type == 2) {
+          for (int slab = 0; slab < p.kslabs; ++slab) {
+            mbar_wait(&full[r.stage], r.phase);
+            tc_fence_after();
+            const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
+            const uint32_t b_addr = a_addr + 16384;
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint64_t da = make_smem_desc(a_addr + ks * 32, 0, 1024, kSwizzle128);         // K-major
+              const uint64_t db = make_smem_desc(b_addr + ks * 1024, 4096, 1024, kSwizzle128);    // MN-major
+              mma_tf32_ss(acc, da, db, idesc_p2, (slab | ks) != 0);
+            }
+            mma_commit(&empty[r.stage]);
+            r.advance();
+          }
+          mma_commit(&tfull[ab]);
+        } else {
+          Ring r0 = r;
+          uint32_t b_addr;
+          if constexpr (D == 128) {
+            mbar_wait(&full[r.stage], r.phase);
+            b_addr = ring_addr + r.stage * kStageBytes;
+            r.advance();
+          }
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            mbar_wait(&full[r.stage], r.phase);
+            tc_fence_after();
+            const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
+            if constexpr (D == 64) { if (sub == 0) b_addr = a_addr + 16384; }
+            for (int ks = 0; ks < D / 16; ++ks) {
+              const uint32_t a_off = (ks >> 2) * 16384 + (ks & 3) * 32;  // K-major: 4 k-steps per 64-channel tile
+              const uint64_t da = make_smem_desc(a_addr + a_off, 0, 1024, kSwizzle128);
+              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 16384, 1024, kSwizzle128);
+              mma_f16_ss(acc + sub * 128, da, db, idesc_p3, ks != 0);
+            }
+            r.advance();
+          }
+          const int ns = p3_stages<D>(p);
+          for (int k = 0; k < ns; ++k) mma_commit(&empty[r0.at(k).stage]);
+          mma_commit(&tfull[ab]);
+        }
+        ++nitem;
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================================================ epilogue warpgroup (TMEM -> regs -> smem -> TMA)
+    const int q4 = warp & 3;                 // TMEM sub-partition (lanes 32*q4 .. 32*q4+31)
+    const int et = threadIdx.x - 128;        // 0..127
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    Ring r;
+    uint32_t nitem = 0;
+    uint32_t nstore = 0;                     // staging buffer toggles per TMA-store chunk
+    uint32_t v[32];
+
+    // write one [rows][128 B] chunk row into the swizzle-128B staging tile
+    auto stage_row = [&](uint8_t* buf, int row, const uint32_t* w32) {
+      uint4* dst = reinterpret_cast<uint4*>(buf + row * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
+    };
+    auto staging_acquire = [&]() -> uint8_t* {
+      // the buffer we are about to overwrite was handed to TMA two chunks ago
+      if (et == 0) tma_store_wait_read<1>();
+      named_bar_sync(1, kEpiThreads);
+      return staging + (nstore & 1) * kStagingBytes;
+    };
+    auto staging_publish = [&]() {
+      fence_proxy_async_smem();
+      named_bar_sync(2, kEpiThreads);
+      ++nstore;
+    };
+
+    while (sched.next(it)) {
+      const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
+      const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
+      if (it.type == 1) {
+        const int j = it.t;
+        mbar_wait(&tfull[ab], aphase);
+        tc_fence_after();
+        // rows of S live in TMEM lanes: D == 128 -> lane = row; D == 64 (M=64 MMA) -> row r in lane 32*(r/16)+r%16
+        const bool row_ok = (D == 128) || (lane < 16);
+        const int row = (D == 128) ? et : (q4 * 16 + (lane & 15));
+        for (int c = 0; c < D / 32; ++c) {
+          tmem_ld_x32(acc + c * 32, v);
+          tmem_ld_wait();
+          uint8_t* buf = staging_acquire();
+          if (row_ok) stage_row(buf, row, v);
+          staging_publish();
+          if (et == 0) {
+            tma_store_3d(&p.tmSst, buf, c * 32, 0, it.g * p.M + j);
+            tma_store_commit();
+          }
+        }
+        if (p.normalize) {
+          uint32_t ks;
+          tmem_ld_x1(acc + kKsumCol, ks);
+          tmem_ld_wait();
+          if (row_ok) ksum_s[row] = __uint_as_float(ks);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
+        const int kvs = (D == 64 ? 1 : 2) + p.ropenorm;
+        r.advance(p.nsub * kvs);
+        if (p.normalize) {
+          named_bar_sync(3, kEpiThreads);  // ksum_s complete
+          float* nloc = p.ws_S + (size_t)(it.g * p.M + j) * p.ncols + D * D;
+          if constexpr (D == 64) {
+            mbar_wait(&full[r.stage], r.phase);
+            const uint8_t* qs = ring + r.stage * kStageBytes;
+            for (int t = et; t < p.wpad; t += kEpiThreads) {
+              float acc_n = 0.f;
+              if (t < p.nsub * p.TW) {
+                const uint4* rowp = reinterpret_cast<const uint4*>(qs + t * 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const uint4 u = rowp[c ^ (t & 7)];
+                  const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    float2 f;
+                    if (p.is_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
+                    else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
+                    acc_n = fmaf(f.x, ksum_s[c * 8 + e * 2], acc_n);
+                    acc_n = fmaf(f.y, ksum_s[c * 8 + e * 2 + 1], acc_n);
+                  }
+                }
+              }
+              nloc[t] = acc_n;
+            }
+            named_bar_sync(1, kEpiThreads);
+            if (et == 0) mbar_arrive(&empty[r.stage]);
+            r.advance();
+          } else {
+            for (int sub = 0; sub < p.nsub; ++sub) {
+              mbar_wait(&full[r.stage], r.phase);
+              const uint8_t* qs = ring + r.stage * kStageBytes;
+              const int t = sub * p.TW + et;
+              if (et < p.TW && t < p.wpad) {
+                float acc_n = 0.f;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint4* rowp = reinterpret_cast<const uint4*>(qs + hh * 16384 + et * 128);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const uint4 u = rowp[c ^ (et & 7)];
+                    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                      float2 f;
+                      if (p.is_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
+                      else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
+                      acc_n = fmaf(f.x, ksum_s[hh * 64 + c * 8 + e * 2], acc_n);
+                      acc_n = fmaf(f.y, ksum_s[hh * 64 + c * 8 + e * 2 + 1], acc_n);
+                    }
+                  }
+                }
+                nloc[t] = acc_n;
+              }
+              named_bar_sync(1, kEpiThreads);
+              if (et == 0) mbar_arrive(&empty[r.stage]);
+              r.advance();
+            }
+            // zero the padding columns [nsub*TW, wpad) if any (none when TW divides wpad)
+            for (int t = p.nsub * p.TW + et; t < p.wpad; t += kEpiThreads) nloc[t] = 0.f;
+          }
+        }
+        if (p.mode == 0) {
+          named_bar_sync(2, kEpiThreads);  // every thread's n_loc stores are issued
+          if (et == 0) {
+            tma_store_wait_all<0>();
+            fence_proxy_async_all();
+            __threadfence();
+            red_release_gpu_add(&p.counters[it.g], 1u);
+          }
+        }
+      } else if (it.type == 2) {
+        const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+        mbar_wait(&tfull[ab], aphase);
+        tc_fence_after();
+        if (tc < p.n2_scols) {
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            uint32_t pk[32];
+            tmem_ld_x32(acc + hlf * 64, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(v[2 * e]), bq = __uint_as_float(v[2 * e + 1]);
+              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[e] = *reinterpret_cast<uint32_t*>(&hv); }
+              else pk[e] = pack_bf16x2(a, bq);
+            }
+            tmem_ld_x32(acc + hlf * 64 + 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(v[2 * e]), bq = __uint_as_float(v[2 * e + 1]);
+              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
+              else pk[16 + e] = pack_bf16x2(a, bq);
+            }
+            uint8_t* buf = staging_acquire();
+            stage_row(buf, et, pk);
+            staging_publish();
+            if (et == 0) {
+              tma_store_3d(&p.tmStst, buf, tc * 128 + hlf * 64, ti * 128, it.g);
+              tma_store_commit();
+            }
+          }
+        } else {
+          for (int q = 0; q < 4; ++q) {
+            tmem_ld_x32(acc + q * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + p.eps);
+            uint8_t* buf = staging_acquire();
+            stage_row(buf, et, v);
+            staging_publish();
+            if (et == 0) {
+              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 128 + q * 32, ti * 128, it.g);
+              tma_store_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
+        r.advance(p.kslabs);
+        if (p.mode == 0 && et == 0) {
+          tma_store_wait_all<0>();
+          fence_proxy_async_all();
+          __threadfence();
+          red_release_gpu_add(&p.counters[p.G + it.g], 1u);
+        }
+      } else {
+        const int i = it.t;
+        float rden[2] = {1.f, 1.f};
+        if (p.normalize) {
+          // den was produced by other CTAs: the producer lane acquired the group counter before issuing this
+          // item's loads; read through L2 (.cg) after the accumulator barrier below orders us behind it.
+        }
+        mbar_wait(&tfull[ab], aphase);
+        tc_fence_after();
+        if (p.normalize) {
+          const float* dg = p.den + (size_t)(it.g * p.M + i) * p.wpad;
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            const int t = sub * p.TW + et;
+            if (et < p.TW && t < p.w) rden[sub] = 1.0f / __ldcg(dg + t);
+          }
+        }
+        for (int sub = 0; sub < p.nsub; ++sub) {
+          for (int c = 0; c < D / 64; ++c) {
+            uint32_t pk[32];
+            tmem_ld_x32(acc + sub * 128 + c * 64, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(v[2 * e]) * rden[sub], bq = __uint_as_float(v[2 * e + 1]) * rden[sub];
+              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[e] = *reinterpret_cast<uint32_t*>(&hv); }
+              else pk[e] = pack_bf16x2(a, bq);
+            }
+            tmem_ld_x32(acc + sub * 128 + c * 64 + 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float a = __uint_as_float(v[2 * e]) * rden[sub], bq = __uint_as_float(v[2 * e + 1]) * rden[sub];
+              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
+              else pk[16 + e] = pack_bf16x2(a, bq);
+            }
+            uint8_t* buf = staging_acquire();
+            stage_row(buf, et, pk);
+            staging_publish();
+            if (et == 0) {
+              const int b = it.g / p.H, h = it.g % p.H;
+              tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, i, h, b);
+              tma_store_commit();
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
+        r.advance(p3_stages<D>(p));
+      }
+      ++nitem;
+    }
+    if (et == 0) tma_store_wait_all<0>();
+  }
+
+  // ---------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// Tiny prologue: copy the mixing matrix into a 16-byte-pitched workspace buffer (optionally keeping only the
+// strictly-lower triangle, for the causal variant) and zero the dependency counters.
+__global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, float* __restrict__ out, int M, int Mp,
+                                int strict_lower, uint32_t* counters, int ncounters) {
+  const int n = M * Mp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int i = idx / Mp, j = idx % Mp;
+    float v = 0.f;
+    if (j < M && (!strict_lower || j < i)) v = mix[(long long)i * ld + j];
+    out[idx] = v;
+  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncounters; idx += gridDim.x * blockDim.x)
+    counters[idx] = 0u;
+}
+
+}  // namespace mhla

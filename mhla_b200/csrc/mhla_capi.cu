@@ -1,0 +1,332 @@
+// C-ABI host side of libmhla_b200.so: argument validation, workspace carving, TMA tensor-map encoding
+// (driver entry point resolved at run time - no link-time dependency on libcuda) and kernel launches.
+// See include/mhla_b200.h for the contract.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mhla_b200.h"
+#include "blockmix_kernel.cuh"
+#include "causal_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_last_cuda_error;
+thread_local int g_last_launches = 0;
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+bool cuda_ok(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  g_last_cuda_error = std::string(what) + ": " + cudaGetErrorString(e);
+  return false;
+}
+
+struct MapSpec {
+  CUtensorMapDataType dt;
+  int rank;
+  void* base;
+  uint64_t dims[5];
+  uint64_t strides[4];  // bytes, dims 1..rank-1
+  uint32_t box[5];
+};
+
+bool encode_map(CUtensorMap* out, const MapSpec& s) {
+  EncodeFn fn = get_encode_fn();
+  if (!fn) { g_last_cuda_error = "cuTensorMapEncodeTiled entry point not found"; return false; }
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  cuuint64_t dims[5], strides[4];
+  cuuint32_t box[5];
+  for (int i = 0; i < s.rank; ++i) { dims[i] = s.dims[i]; box[i] = s.box[i]; }
+  for (int i = 0; i + 1 < s.rank; ++i) strides[i] = s.strides[i];
+  CUresult r = fn(out, s.dt, (cuuint32_t)s.rank, s.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): rank %d dims %llu %llu %llu %llu %llu box %u %u %u",
+             (int)r, s.rank, (unsigned long long)s.dims[0], (unsigned long long)s.dims[1],
+             (unsigned long long)s.dims[2], (unsigned long long)s.dims[3], (unsigned long long)s.dims[4], s.box[0],
+             s.box[1], s.box[2]);
+    g_last_cuda_error = buf;
+    return false;
+  }
+  return true;
+}
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------ blockmix
+struct BlockmixPlan {
+  int G, TW, nsub, wpad, ncols, Mp, n2_rows, n2_cols, n2_scols, kslabs, normalize, ropenorm;
+  size_t off_S, off_St, off_den, off_W, off_cnt, total;
+};
+
+int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
+  if (!d) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->B < 1 || d->H < 1 || d->M < 1 || d->w < 1) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->D != 64 && d->D != 128) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->w > 256) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  const int D = d->D;
+  pl->G = d->B * d->H;
+  pl->TW = d->w >= 128 ? 128 : (d->w + 15) / 16 * 16;
+  pl->nsub = (d->w + pl->TW - 1) / pl->TW;
+  pl->normalize = (d->flags & MHLA_FLAG_NORMALIZE) ? 1 : 0;
+  pl->ropenorm = (pl->normalize && d->k_rope.ptr != nullptr) ? 1 : 0;
+  pl->wpad = pl->normalize ? (pl->nsub * pl->TW) : 0;
+  pl->ncols = D * D + pl->wpad;
+  pl->Mp = (d->M + 3) / 4 * 4;
+  pl->n2_rows = (d->M + 127) / 128;
+  pl->n2_scols = D * D / 128;
+  pl->n2_cols = pl->n2_scols + (pl->wpad + 127) / 128;
+  pl->kslabs = (d->M + 31) / 32;
+  size_t off = 0;
+  const size_t GM = (size_t)pl->G * d->M;
+  pl->off_S = off;   off = align_up(off + GM * pl->ncols * 4, 1024);
+  pl->off_St = off;  off = align_up(off + GM * D * D * 2, 1024);
+  pl->off_den = off; off = align_up(off + GM * (pl->wpad ? pl->wpad : 32) * 4, 1024);
+  pl->off_W = off;   off = align_up(off + (size_t)d->M * pl->Mp * 4, 1024);
+  pl->off_cnt = off; off = align_up(off + (size_t)2 * pl->G * 4, 1024);
+  pl->total = off;
+  return MHLA_OK;
+}
+
+bool t5_ok(const mhla_tensor5& t) {
+  if ((reinterpret_cast<uintptr_t>(t.ptr) & 15) != 0) return false;
+  return t.stride_b % 8 == 0 && t.stride_h % 8 == 0 && t.stride_m % 8 == 0 && t.stride_w % 8 == 0;
+}
+
+MapSpec spec_t5(const mhla_tensor5& t, const mhla_blockmix_desc* d, int TW) {
+  MapSpec s{};
+  s.dt = d->dtype == MHLA_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  s.rank = 5;
+  s.base = const_cast<void*>(t.ptr);
+  const uint64_t dims[5] = {(uint64_t)d->D, (uint64_t)d->w, (uint64_t)d->M, (uint64_t)d->H, (uint64_t)d->B};
+  int64_t str[4] = {t.stride_w, t.stride_m, t.stride_h, t.stride_b};
+  for (int i = 0; i < 5; ++i) s.dims[i] = dims[i];
+  uint64_t prev = (uint64_t)d->D * 2;  // a valid (16-byte multiple) stand-in for size-1 dimensions
+  for (int i = 0; i < 4; ++i) {
+    uint64_t bytes = (uint64_t)str[i] * 2;
+    if (dims[i + 1] == 1 || bytes == 0) bytes = prev;
+    s.strides[i] = bytes;
+    prev = bytes * dims[i + 1];
+  }
+  s.box[0] = 64; s.box[1] = (uint32_t)TW; s.box[2] = s.box[3] = s.box[4] = 1;
+  return s;
+}
+
+struct CacheEntry {
+  mhla_blockmix_desc key;
+  mhla::BlockmixParams params;
+};
+std::mutex g_cache_mu;
+std::vector<CacheEntry> g_cache;
+
+int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, mhla::BlockmixParams* P) {
+  const int D = d->D;
+  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
+  float* S = reinterpret_cast<float*>(ws + pl.off_S);
+  void* St = ws + pl.off_St;
+  float* den = reinterpret_cast<float*>(ws + pl.off_den);
+  float* Wp = reinterpret_cast<float*>(ws + pl.off_W);
+  const uint64_t GM = (uint64_t)pl.G * d->M;
+  const CUtensorMapDataType dt16 =
+      d->dtype == MHLA_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const bool rope = d->k_rope.ptr != nullptr;
+
+  if (!encode_map(&P->tmK, spec_t5(rope ? d->k_rope : d->k, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!encode_map(&P->tmV, spec_t5(d->v, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!encode_map(&P->tmKn, spec_t5(d->k, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!encode_map(&P->tmQn, spec_t5(d->q, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!encode_map(&P->tmQr, spec_t5(d->q_rope.ptr ? d->q_rope : d->q, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!encode_map(&P->tmO, spec_t5(d->out, d, pl.TW))) return MHLA_ERR_CUDA;
+  {
+    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, S, {(uint64_t)D, (uint64_t)D, GM},
+              {(uint64_t)D * 4, (uint64_t)pl.ncols * 4}, {32, (uint32_t)D, 1}};
+    if (!encode_map(&P->tmSst, s)) return MHLA_ERR_CUDA;
+  }
+  {
+    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, S, {(uint64_t)pl.ncols, (uint64_t)d->M, (uint64_t)pl.G},
+              {(uint64_t)pl.ncols * 4, (uint64_t)d->M * pl.ncols * 4}, {32, 32, 1}};
+    if (!encode_map(&P->tmSld, s)) return MHLA_ERR_CUDA;
+  }
+  {
+    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Wp, {(uint64_t)pl.Mp, (uint64_t)d->M}, {(uint64_t)pl.Mp * 4},
+              {32, 128}};
+    if (!encode_map(&P->tmW, s)) return MHLA_ERR_CUDA;
+  }
+  {
+    MapSpec s{dt16, 3, St, {(uint64_t)D * D, (uint64_t)d->M, (uint64_t)pl.G},
+              {(uint64_t)D * D * 2, (uint64_t)d->M * D * D * 2}, {64, 128, 1}};
+    if (!encode_map(&P->tmStst, s)) return MHLA_ERR_CUDA;
+  }
+  {
+    const uint64_t wp = pl.wpad ? pl.wpad : 32;
+    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, den, {wp, (uint64_t)d->M, (uint64_t)pl.G},
+              {wp * 4, (uint64_t)d->M * wp * 4}, {32, 128, 1}};
+    if (!encode_map(&P->tmDen, s)) return MHLA_ERR_CUDA;
+  }
+  {
+    MapSpec s{dt16, 3, St, {(uint64_t)D, (uint64_t)D, GM}, {(uint64_t)D * 2, (uint64_t)D * D * 2},
+              {64, (uint32_t)D, 1}};
+    if (!encode_map(&P->tmStld, s)) return MHLA_ERR_CUDA;
+  }
+  P->ws_S = S;
+  P->den = den;
+  P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+  P->G = pl.G; P->H = d->H; P->M = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
+  P->ncols = pl.ncols; P->wpad = pl.wpad;
+  P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
+  P->normalize = pl.normalize; P->ropenorm = pl.ropenorm; P->is_fp16 = d->dtype == MHLA_FP16;
+  P->mode = 0; P->lag2 = 1; P->lag3 = 3;
+  P->eps = d->eps;
+  (void)Wp;
+  return MHLA_OK;
+}
+
+int g_num_sms = 0;
+bool g_attr_set64 = false, g_attr_set128 = false;
+
+}  // namespace
+
+extern "C" {
+
+int mhla_abi_version(void) { return MHLA_B200_ABI_VERSION; }
+
+const char* mhla_strerror(int status) {
+  switch (status) {
+    case MHLA_OK: return "ok";
+    case MHLA_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case MHLA_ERR_UNSUPPORTED_SHAPE: return "shape outside the supported envelope";
+    case MHLA_ERR_ALIGNMENT: return "pointer or stride alignment";
+    case MHLA_ERR_WORKSPACE: return "workspace missing or too small";
+    case MHLA_ERR_CUDA: return "CUDA error";
+    case MHLA_ERR_NO_DEVICE: return "current device is not an sm_100 GPU";
+    default: return "unknown status";
+  }
+}
+
+const char* mhla_last_cuda_error(void) { return g_last_cuda_error.c_str(); }
+int mhla_last_launch_count(void) { return g_last_launches; }
+
+size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc) {
+  BlockmixPlan pl;
+  if (plan_blockmix(desc, &pl) != MHLA_OK) return 0;
+  return pl.total;
+}
+
+int mhla_blockmix_workspace_layout(const mhla_blockmix_desc* desc, size_t out[8]) {
+  BlockmixPlan pl;
+  int rc = plan_blockmix(desc, &pl);
+  if (rc != MHLA_OK) return rc;
+  out[0] = pl.off_S; out[1] = pl.off_St; out[2] = pl.off_den; out[3] = pl.off_W; out[4] = pl.off_cnt;
+  out[5] = (size_t)pl.ncols; out[6] = (size_t)pl.wpad; out[7] = (size_t)pl.Mp;
+  return MHLA_OK;
+}
+
+int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
+  BlockmixPlan pl;
+  int rc = plan_blockmix(d, &pl);
+  if (rc != MHLA_OK) return rc;
+  if (!d->q.ptr || !d->k.ptr || !d->v.ptr || !d->out.ptr || !d->mix) return MHLA_ERR_INVALID_ARGUMENT;
+  if ((d->q_rope.ptr == nullptr) != (d->k_rope.ptr == nullptr)) return MHLA_ERR_INVALID_ARGUMENT;
+  if (!d->workspace || d->workspace_bytes < pl.total) return MHLA_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(d->workspace) & 1023) != 0) return MHLA_ERR_ALIGNMENT;
+  if (!t5_ok(d->q) || !t5_ok(d->k) || !t5_ok(d->v) || !t5_ok(d->out)) return MHLA_ERR_ALIGNMENT;
+  if (d->q_rope.ptr && (!t5_ok(d->q_rope) || !t5_ok(d->k_rope))) return MHLA_ERR_ALIGNMENT;
+  if (d->mix_ld < d->M) return MHLA_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+
+  if (g_num_sms == 0) {
+    int dev = 0, major = 0, sms = 0;
+    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return MHLA_ERR_CUDA;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10) return MHLA_ERR_NO_DEVICE;
+    g_num_sms = sms;
+  }
+
+  mhla::BlockmixParams P;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    bool hit = false;
+    for (auto& e : g_cache)
+      if (std::memcmp(&e.key, d, sizeof(*d)) == 0) { P = e.params; hit = true; break; }
+    if (!hit) {
+      std::memset(&P, 0, sizeof P);
+      rc = build_blockmix_params(d, pl, &P);
+      if (rc != MHLA_OK) return rc;
+      if (g_cache.size() >= 32) g_cache.erase(g_cache.begin());
+      CacheEntry e;
+      std::memcpy(&e.key, d, sizeof(*d));
+      e.params = P;
+      g_cache.push_back(e);
+    }
+  }
+
+  auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
+  bool& attr = d->D == 64 ? g_attr_set64 : g_attr_set128;
+  if (!attr) {
+    if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
+                 "cudaFuncSetAttribute"))
+      return MHLA_ERR_CUDA;
+    attr = true;
+  }
+
+  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
+  int launches = 0;
+  mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mix, (long long)d->mix_ld, reinterpret_cast<float*>(ws + pl.off_W),
+                                               d->M, pl.Mp, 0, P.counters, 2 * pl.G);
+  ++launches;
+  const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
+  if (d->flags & MHLA_FLAG_UNFUSED) {
+    const int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
+    for (int mode = 1; mode <= last; ++mode) {
+      P.mode = mode;
+      const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
+      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+      kern<<<grid, mhla::kThreads, mhla::kSmemAlloc, stream>>>(P);
+      ++launches;
+    }
+  } else {
+    P.mode = 0;
+    const long long items = (long long)pl.G * (n1 + n2 + n3);
+    const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+    kern<<<grid, mhla::kThreads, mhla::kSmemAlloc, stream>>>(P);
+    ++launches;
+  }
+  if (!cuda_ok(cudaGetLastError(), "kernel launch")) return MHLA_ERR_CUDA;
+  g_last_launches = launches;
+  return MHLA_OK;
+}
+
+size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }
+
+int mhla_fwd_causal(const mhla_causal_desc* desc, void* stream) {
+  int launches = 0;
+  int rc = mhla::causal_forward(desc, static_cast<cudaStream_t>(stream), &launches, &g_last_cuda_error);
+  if (rc == MHLA_OK) g_last_launches = launches;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+"""Functional API of the B200-native MHLA forward operator.
+
+``mhla(q, k, v, mix, ...)`` is the block-mixed operator the reference writes inline
+(mhla_dit/mhla/mhla.py:262-268; mhla_videogen/diffusion/model/wan/mhla_utils.py:328-341);
+``naive_chunk_simple_mhla_fixed`` / ``naive_recurrent_mhla`` keep the reference's causal entry points
+(mhla_nlp/fla/ops/mhla/naive.py:10-83, :88-142) name-for-name so ``fla.layers.mhla`` can import them unchanged.
+
+Everything here is a thin host shim: argument checking, output/workspace allocation from the torch caching
+allocator, and one C-ABI call (``libmhla_b200.so``) on the current CUDA stream.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _capi
+
+__all__ = ["mhla", "mhla_blockmix", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+           "last_launch_count"]
+
+_DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("mhla_b200 operators run on CUDA (sm_100a) tensors only; there is no CPU fallback")
+
+
+def _as5(t: torch.Tensor) -> torch.Tensor:
+    """View as [B, H, M, w, D]; the reference's '(b h) n w d' 4-D layout becomes H = 1."""
+    if t.dim() == 4:
+        return t.unsqueeze(1)
+    if t.dim() != 5:
+        raise ValueError(f"expected a [B,H,M,w,D] or [(B H),M,w,D] tensor, got shape {tuple(t.shape)}")
+    return t
+
+
+def _tma_ok(t: torch.Tensor) -> bool:
+    if t.stride(-1) != 1 or t.data_ptr() % 16:
+        return False
+    return all(s % 8 == 0 for s, n in zip(t.stride()[:-1], t.shape[:-1]) if n > 1)
+
+
+def _prep(t: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    t = _as5(t)
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    if not _tma_ok(t):
+        t = t.contiguous()
+    return t
+
+
+def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
+    if t is None:
+        return _capi.Tensor5(None, 0, 0, 0, 0)
+    sb, sh, sm, sw, _ = t.stride()
+    return _capi.Tensor5(t.data_ptr(), sb, sh, sm, sw)
+
+
+def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
+                  out: Optional[torch.Tensor] = None, unfused: bool = False) -> torch.Tensor:
+    """Non-causal block-mixed MHLA forward on block-major tensors.
+
+    q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
+              with fp32 accumulation and returned as fp32).  Strided views are consumed in place when every
+              stride is a multiple of 8 elements.
+    mix     : [M, M] (or the Conv2d weight [M, M, 1, 1]); out_i = sum_j mix[i, j] (.)_j.
+    q_rope, k_rope : roped copies for the numerator (variant B); q, k then only feed the normaliser.
+    """
+    _require_cuda(q, k, v, mix, q_rope, k_rope)
+    if (q_rope is None) != (k_rope is None):
+        raise ValueError("q_rope and k_rope must be given together")
+    in_dtype = q.dtype
+    cdtype = in_dtype if in_dtype in _DT else torch.bfloat16
+    squeeze = q.dim() == 4
+    q5, k5, v5 = _prep(q, cdtype), _prep(k, cdtype), _prep(v, cdtype)
+    qr5, kr5 = _prep(q_rope, cdtype), _prep(k_rope, cdtype)
+    B, H, M, w, D = q5.shape
+    for name, t in (("k", k5), ("v", v5), ("q_rope", qr5), ("k_rope", kr5)):
+        if t is not None and tuple(t.shape) != (B, H, M, w, D):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {(B, H, M, w, D)}")
+    mix2 = mix.reshape(mix.shape[0], mix.shape[1]) if mix.dim() != 2 else mix
+    if tuple(mix2.shape) != (M, M):
+        raise ValueError(f"mix must be [{M}, {M}], got {tuple(mix.shape)}")
+    mix2 = mix2.detach().to(torch.float32).contiguous()
+    if out is None:
+        o5 = torch.empty((B, H, M, w, D), dtype=cdtype, device=q.device)
+    else:
+        o5 = _as5(out)
+        if o5.dtype != cdtype or not _tma_ok(o5) or tuple(o5.shape) != (B, H, M, w, D):
+            raise ValueError("out must be a TMA-compatible tensor of the compute dtype and the shape of q")
+
+    d = _capi.BlockmixDesc()
+    d.B, d.H, d.M, d.w, d.D = B, H, M, w, D
+    d.dtype = _DT[cdtype]
+    d.flags = (_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if unfused else 0)
+    d.eps = float(eps)
+    d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
+    d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)
+    d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
+    L = _capi.lib()
+    nbytes = L.mhla_blockmix_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise _capi.MhlaError(f"unsupported blockmix shape B={B} H={H} M={M} w={w} D={D} (need D in {{64,128}}, w<=256)")
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024
+    d.workspace, d.workspace_bytes = base, nbytes
+    with torch.cuda.device(q.device):
+        _capi.check(L.mhla_fwd_blockmix(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_blockmix")
+    # keep the operands alive until the stream has consumed them
+    for t in (q5, k5, v5, qr5, kr5, mix2, ws):
+        if t is not None:
+            t.record_stream(torch.cuda.current_stream())
+    res = o5 if out is None else out
+    if out is None:
+        if squeeze:
+            res = res.squeeze(1)
+        if in_dtype != cdtype:
+            res = res.to(in_dtype)
+    return res
+
+
+def _t4(t: torch.Tensor) -> _capi.Tensor4:
+    sb, st, sh, _ = t.stride()
+    return _capi.Tensor4(t.data_ptr(), sb, st, sh)
+
+
+def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None) -> torch.Tensor:
+    """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype."""
+    _require_cuda(q, k, v, mixing_matrix)
+    in_dtype = q.dtype
+    cdtype = in_dtype if in_dtype in _DT else torch.bfloat16
+    B, T, H, K = q.shape
+    V = v.shape[-1]
+
+    def prep(t):
+        t = t.to(cdtype) if t.dtype != cdtype else t
+        return t if _tma_ok(t) else t.contiguous()
+
+    q4, k4, v4 = prep(q), prep(k), prep(v)
+    o4 = torch.empty((B, T, H, V), dtype=cdtype, device=q.device)
+    Lm = mixing_matrix.shape[0]
+    mm = mixing_matrix.detach().reshape(Lm, mixing_matrix.shape[1]).to(torch.float32).contiguous()
+    n = (T + chunk_size - 1) // chunk_size
+    if n > Lm:
+        raise IndexError(f"mixing matrix is {Lm}x{Lm} but T={T} needs {n} chunks of {chunk_size}")
+    d = _capi.CausalDesc()
+    d.B, d.T, d.H, d.K, d.V = B, T, H, K, V
+    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], 0
+    d.scale = float(K ** -0.5 if scale is None else scale)
+    d.q, d.k, d.v, d.out = _t4(q4), _t4(k4), _t4(v4), _t4(o4)
+    d.mm, d.mm_ld, d.L = mm.data_ptr(), mm.stride(0), Lm
+    L = _capi.lib()
+    nbytes = L.mhla_causal_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise _capi.MhlaError(f"unsupported causal shape T={T} K={K} V={V} chunk={chunk_size}")
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
+    with torch.cuda.device(q.device):
+        _capi.check(L.mhla_fwd_causal(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_causal")
+    for t in (q4, k4, v4, mm, ws):
+        t.record_stream(torch.cuda.current_stream())
+    return o4 if in_dtype == cdtype else o4.to(in_dtype)
+
+
+def mhla(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
+         causal: bool = False, chunk: Optional[int] = None, **kw) -> torch.Tensor:
+    """The operator signature SURVEY.md 8b defines: one entry point for the three reference variants."""
+    if causal:
+        return mhla_causal(q, k, v, mix, chunk_size=chunk or 64)
+    return mhla_blockmix(q, k, v, mix, q_rope=q_rope, k_rope=k_rope, eps=eps, normalize=normalize, **kw)
+
+
+def naive_chunk_simple_mhla_fixed(q, k, v, mixing_matrix, output_final_state: bool = False, chunk_size: int = 64,
+                                  *args, **kwargs):
+    """Drop-in for mhla_nlp/fla/ops/mhla/naive.py:10-83 (returns o only; ``output_final_state`` is a no-op there too)."""
+    return mhla_causal(q, k, v, mixing_matrix, chunk_size=chunk_size)
+
+
+def naive_recurrent_mhla(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
+                         initial_state=None, output_final_state: bool = True):
+    """Drop-in for naive.py:88-142.  The layer only selects it for q_len <= 64 (layers/mhla.py:247), where it equals
+    the chunk form; beyond one chunk the reference's recurrence is inconsistent and its returned state is all zeros
+    (SURVEY.md 0.4), so this raises instead of reproducing the bug.  Returns (o, None)."""
+    if q.shape[1] > chunk_size:
+        raise ValueError("naive_recurrent_mhla is only defined for T <= chunk_size (reference defect, SURVEY.md 0.4)")
+    if initial_state is not None:
+        raise NotImplementedError("initial_state is not supported (the reference never produces a usable state)")
+    return mhla_causal(q, k, v, mixing_matrix, chunk_size=chunk_size, scale=scale), None
+
+
+def last_launch_count() -> int:
+    return int(_capi.lib().mhla_last_launch_count())
