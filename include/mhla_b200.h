@@ -44,7 +44,8 @@ enum {
   MHLA_FLAG_NORMALIZE = 1 << 0, /* divide by the (quirky) block-mixed normaliser, mhla.py:265-268 */
   MHLA_FLAG_UNFUSED = 1 << 8,   /* debugging: run the three phases as separate launches */
   MHLA_FLAG_STOP_AFTER_P1 = 1 << 9,  /* debugging (with UNFUSED): stop after the block summaries */
-  MHLA_FLAG_STOP_AFTER_P2 = 1 << 10  /* debugging (with UNFUSED): stop after the block mixing */
+  MHLA_FLAG_STOP_AFTER_P2 = 1 << 10, /* debugging (with UNFUSED): stop after the block mixing */
+  MHLA_FLAG_ONLY_P3 = 1 << 11        /* debugging (with UNFUSED): run only the readout on a caller-filled workspace */
 };
 
 /*

@@ -13,6 +13,7 @@ FLAG_NORMALIZE = 1 << 0
 FLAG_UNFUSED = 1 << 8
 FLAG_STOP_AFTER_P1 = 1 << 9
 FLAG_STOP_AFTER_P2 = 1 << 10
+FLAG_ONLY_P3 = 1 << 11
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",

@@ -301,7 +301,8 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
   if (d->flags & MHLA_FLAG_UNFUSED) {
     const int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
-    for (int mode = 1; mode <= last; ++mode) {
+    const int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
+    for (int mode = first; mode <= last; ++mode) {
       P.mode = mode;
       const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);

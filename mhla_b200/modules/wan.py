@@ -1,0 +1,161 @@
+"""Variant-B module: ``MHLA_Video_Uni`` (mhla_videogen/diffusion/model/wan/mhla_utils.py:158-366).
+
+Same constructor signature (including the odd positional call ``cls(dim, num_heads, window_size, qk_norm, eps, ...)``
+of wan/model.py:1644-1646, whose third positional lands in ``dim_head`` and is ignored), attributes and
+``state_dict`` keys (q,k,v,o,[g],norm_q,norm_k,g_norm,block_attn.conv.weight,[lepe]).  The operator core
+(:328-341) is the CUDA kernel; RoPE is evaluated in fp32 real arithmetic on the GPU instead of the reference's
+complex128 per-sample Python loop (:127-156).
+"""
+from __future__ import annotations
+
+import torch
+from einops import rearrange
+from torch import nn
+
+from ..mixing import BlockDistanceConv3D
+from ..ops import mhla_blockmix
+
+
+class WanRMSNorm(nn.Module):
+    """wan/model.py:181-196."""
+
+    def __init__(self, dim, eps=1e-5):
+        super().__init__()
+        self.dim = dim
+        self.eps = eps
+        self.weight = nn.Parameter(torch.ones(dim))
+
+    def forward(self, x):
+        return self._norm(x.float()).type_as(x) * self.weight
+
+    def _norm(self, x):
+        return x * torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + self.eps)
+
+
+_ROPE_CACHE = {}
+
+
+def _rope_tables(grid, freqs: torch.Tensor, device):
+    """cos/sin [N, D/2] for a (F, H, W) token grid from the reference's complex table [1024, D/2] (wan/model.py:1933-1936)."""
+    f, h, w = grid
+    key = (f, h, w, freqs.data_ptr(), freqs.shape[1], str(device))
+    hit = _ROPE_CACHE.get(key)
+    if hit is not None:
+        return hit
+    c = freqs.shape[1]
+    fr = freqs.split([c - 2 * (c // 3), c // 3, c // 3], dim=1)
+    fi = torch.cat([
+        fr[0][:f].view(f, 1, 1, -1).expand(f, h, w, -1),
+        fr[1][:h].view(1, h, 1, -1).expand(f, h, w, -1),
+        fr[2][:w].view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+    cos = fi.real.to(device=device, dtype=torch.float32).contiguous()
+    sin = fi.imag.to(device=device, dtype=torch.float32).contiguous()
+    if len(_ROPE_CACHE) > 8:
+        _ROPE_CACHE.clear()
+    _ROPE_CACHE[key] = (cos, sin)
+    return cos, sin
+
+
+def rope_apply(x: torch.Tensor, grid_sizes, freqs: torch.Tensor) -> torch.Tensor:
+    """x [B, N, H, D] -> fp32 roped tensor; interleaved-pair rotation (mhla_utils.py:127-156).  Every sample uses the
+    grid of sample 0, as the module does (:297)."""
+    g0 = grid_sizes[0]
+    grid = tuple(int(v) for v in (g0.tolist() if torch.is_tensor(g0) else g0))
+    B, N, H, D = x.shape
+    seq = grid[0] * grid[1] * grid[2]
+    cos, sin = _rope_tables(grid, freqs, x.device)
+    xf = x.float()
+    xr = xf[:, :seq].reshape(B, seq, H, D // 2, 2)
+    a, b = xr[..., 0], xr[..., 1]
+    c, s = cos[None, :, None, :], sin[None, :, None, :]
+    out = torch.stack((a * c - b * s, a * s + b * c), dim=-1).reshape(B, seq, H, D)
+    if seq < N:
+        out = torch.cat([out, xf[:, seq:]], dim=1)
+    return out
+
+
+class MHLA_Video_Uni(nn.Module):
+    def __init__(self, dim, num_heads=8, dim_head=None, dropout=0.1, fixed_weight_value=None, qk_norm=True,
+                 block_layout=(3, 5, 10), transform="linear", qkv_bias=False, eps=1e-6, is_gated=False, is_lepe=False,
+                 **kwargs):
+        super().__init__()
+        dim_head = dim // num_heads
+        self.dim = dim
+        self.num_heads = num_heads
+        self.head_dim = dim_head
+        self.q = nn.Linear(dim, dim)
+        self.k = nn.Linear(dim, dim)
+        self.v = nn.Linear(dim, dim)
+        self.g = nn.Linear(dim, dim) if is_gated else None
+        self.g_fn = nn.SiLU() if is_gated else None
+        self.g_norm = WanRMSNorm(dim_head, eps=eps)
+        self.is_gated = is_gated
+        self.is_lepe = is_lepe
+        self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+        self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
+        self.out_norm = kwargs.get("out_rmsnorm", False)
+        self.normalize_out = kwargs.get("normalize_out", True)
+        self.blocks_layout = tuple(block_layout)
+        self.num_blocks = self.blocks_layout[0] * self.blocks_layout[1] * self.blocks_layout[2]
+        self.block_attn = BlockDistanceConv3D(blocks_layout=self.blocks_layout, transform=transform)
+        self.lepe = nn.Conv3d(dim, dim, kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1), groups=dim) if is_lepe else None
+        self.eps = eps
+        self.o = nn.Linear(dim, dim)
+        self.rope_after = kwargs.get("rope_after", False)
+        self.power = kwargs.get("power", 1.0)
+        self.without_rope = kwargs.get("without_rope", False)
+        if fixed_weight_value is not None:
+            self._init_weights_with_fixed_value(fixed_weight_value)
+
+    def _init_weights_with_fixed_value(self, value):
+        for name, param in self.named_parameters():
+            if "weight" in name:
+                nn.init.constant_(param, value)
+            elif "bias" in name and param is not None:
+                nn.init.zeros_(param)
+
+    @staticmethod
+    def init_to_value(model, value=1.0):
+        for name, param in model.named_parameters():
+            if "weight" in name:
+                nn.init.constant_(param, value)
+            elif "bias" in name and param is not None:
+                nn.init.zeros_(param)
+        return model
+
+    def forward(self, x: torch.Tensor, seq_lens, grid_sizes, freqs) -> torch.Tensor:
+        B, N, C = x.shape
+        g0 = grid_sizes[0]
+        F_, H_, W_ = (int(v) for v in (g0.tolist() if torch.is_tensor(g0) else g0))
+        fb, hb, wb = self.blocks_layout
+        p1, p2, p3 = F_ // fb, H_ // hb, W_ // wb
+        nh, D = self.num_heads, self.head_dim
+
+        q, k, v = self.q(x), self.k(x), self.v(x)                                   # :279-288
+        lepe = None
+        if self.is_lepe:
+            lepe = self.lepe(rearrange(v, "b (f h w) c -> b c f h w", f=F_, h=H_, w=W_))
+            lepe = rearrange(lepe, "b c f h w -> b (f h w) c")
+        dtype = q.dtype
+        q = torch.relu(self.norm_q(q.float())) + self.eps                          # :308, 267-276
+        k = torch.relu(self.norm_k(k.float())) + self.eps
+        q, k, v = (t.view(B, N, nh, D) for t in (q, k, v))
+        q_rope, k_rope = rope_apply(q, grid_sizes, freqs), rope_apply(k, grid_sizes, freqs)   # :314
+
+        cdtype = torch.float16 if dtype == torch.float16 else torch.bfloat16
+        pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
+        kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
+        blk = lambda t: rearrange(t.to(cdtype), pat, **kw).contiguous()           # noqa: E731  (:317-326, one 16-bit copy each)
+        if self.normalize_out:
+            out = mhla_blockmix(blk(q), blk(k), blk(v), self.block_attn.conv.weight, q_rope=blk(q_rope),
+                                k_rope=blk(k_rope), eps=self.eps, normalize=True)
+        else:  # shipped Wan config (norm_output: false): the un-roped q/k are not needed at all
+            out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), self.block_attn.conv.weight, eps=self.eps,
+                                normalize=False)
+        out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
+        out = self.g_norm(out).reshape(B, N, C)                                     # :360-364 per-head RMSNorm
+        if self.is_gated:
+            out = out * self.g_fn(self.g(x))
+        if self.is_lepe:
+            out = out + lepe
+        return self.o(out)

@@ -1,0 +1,122 @@
+"""Drop-in modules: constructor / state_dict compatibility with the reference (CPU) and forward parity against the
+reference modules' recorded outputs (GPU; fixtures from tests/golden/make_golden.py)."""
+import pytest
+import torch
+
+import oracle
+from conftest import load_golden
+from mhla_b200.modules import MHLA, MHLA4DiT, MHLA_Normed_Torch, MHLA_Video_Uni, rope_apply
+
+
+def _sd(g):
+    return {k[3:]: v for k, v in g.items() if k.startswith("sd.")}
+
+
+def _build(name, g):
+    if name in ("a_dit_s2", "a_qknorm"):
+        dim = g["x"].shape[-1]
+        return MHLA4DiT(dim, heads=int(g["heads"]), dropout=0.0, qk_norm=bool(g["qk_norm"]),
+                        block_size=int(g["block_size"]), embed_len=int(g["embed_len"]), qkv_bias=True)
+    if name == "a_vit_twin":
+        return MHLA_Normed_Torch(g["x"].shape[-1], heads=int(g["heads"]), dropout=0.0, qk_norm=True,
+                                 window_size=int(g["window_size"]), embed_len=int(g["embed_len"]))
+    if name in ("b_norm", "b_nonorm"):
+        return MHLA_Video_Uni(g["x"].shape[-1], int(g["heads"]), None, 0.0, None, True,
+                              tuple(int(v) for v in g["layout"]), normalize_out=bool(g["normalize_out"]),
+                              is_gated=bool(g["gated"]))
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["a_dit_s2", "a_qknorm", "a_vit_twin", "b_norm", "b_nonorm"])
+def test_state_dict_keys_match_reference(name):
+    g = load_golden(name)
+    m = _build(name, g)
+    sd = _sd(g)
+    assert set(m.state_dict().keys()) == set(sd.keys())
+    for k, v in m.state_dict().items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    m.load_state_dict(sd, strict=True)
+
+
+def test_nlp_layer_state_dict_and_init():
+    m = MHLA(mode="chunk", hidden_size=256, expand_k=0.5, expand_v=1.0, num_heads=2, feature_map="relu")
+    keys = set(m.state_dict().keys())
+    assert keys == {"q_proj.weight", "k_proj.weight", "v_proj.weight", "g_proj.weight", "o_proj.weight",
+                    "mixing_matrix", "g_norm_swish_gate.weight"}
+    mm = m.mixing_matrix.view(32, 32)
+    assert tuple(m.mixing_matrix.shape) == (32, 32, 1, 1, 1, 1)
+    torch.testing.assert_close(mm[5, :6], torch.full((6,), 1 / 6))
+    assert float(mm.triu(1).abs().max()) == 0.0
+    m2 = MHLA(hidden_size=256, num_heads=2, feature_map="relu", use_short_conv=True, use_output_gate=False)
+    assert {"q_conv1d.weight", "k_conv1d.weight", "v_conv1d.weight", "g_norm.weight"} <= set(m2.state_dict().keys())
+    with pytest.raises(NotImplementedError):
+        MHLA(feature_map="nope")
+
+
+def test_mixing_modules_match_reference_weights():
+    import mhla_b200
+    g2, g3 = load_golden("blockdist2d"), load_golden("blockdist3d")
+    bd = mhla_b200.BlockDistanceConv(num_patches_per_side=16, patch_group_size=16, transform="linear")
+    torch.testing.assert_close(bd.get_weight_matrix(), g2["W_side16_group16_linear"], rtol=1e-6, atol=1e-7)
+    assert tuple(bd.conv.weight.shape) == (16, 16, 1, 1)
+    bd3 = mhla_b200.BlockDistanceConv3D(blocks_layout=(3, 5, 10), transform="linear")
+    torch.testing.assert_close(bd3.get_weight_matrix(), g3["W_3x5x10_linear"], rtol=1e-6, atol=1e-7)
+    with pytest.raises(ValueError):
+        mhla_b200.BlockDistanceConv3D(transform="bogus")
+
+
+@pytest.mark.parametrize("name", ["b_norm", "b_nonorm"])
+def test_rope_real_arithmetic_matches_reference(name):
+    g = load_golden(name)
+    d = g["q_tok"].shape[-1]
+    freqs = oracle.rope_freqs_wan(d)
+    grid = torch.tensor([[int(v) for v in g["grid"]]] * g["q_tok"].shape[0])
+    torch.testing.assert_close(rope_apply(g["q_tok"], grid, freqs), g["q_rope_tok"], rtol=1e-5, atol=1e-5)
+
+
+def test_ops_refuse_cpu_tensors():
+    import mhla_b200
+    q = torch.zeros(1, 1, 2, 16, 64, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        mhla_b200.mhla(q, q, q, torch.eye(2))
+
+
+# ------------------------------------------------------------------------------------------------ GPU forward parity
+def _fwd_err(name, atol_scale=1.0):
+    g = load_golden(name)
+    m = _build(name, g).eval()
+    m.load_state_dict(_sd(g), strict=True)
+    m = m.cuda()
+    x = g["x"].cuda()
+    with torch.no_grad():
+        if name.startswith("b_"):
+            B = x.shape[0]
+            grid = torch.tensor([[int(v) for v in g["grid"]]] * B, dtype=torch.long)
+            d = x.shape[-1] // int(g["heads"])
+            y = m(x, torch.tensor([x.shape[1]] * B), grid, oracle.rope_freqs_wan(d))
+        else:
+            y = m(x)
+    torch.cuda.synchronize()
+    return oracle.err_ratio(g["y"], y.float().cpu())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["a_dit_s2", "b_nonorm"])
+def test_module_forward_matches_reference_module(name):
+    """Whole-module forward (fp32 weights, operator in bf16) vs the reference module's recorded fp32 output.
+    Budget: the operator's 5e-3 plus bf16 rounding of q,k,v (2^-9 each)."""
+    assert _fwd_err(name) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_dit_module_accepts_3d_tokens():
+    g = load_golden("a_dit_s2")
+    m = _build("a_dit_s2", g).eval()
+    m.load_state_dict(_sd(g))
+    m = m.cuda()
+    x = g["x"].cuda()
+    with torch.no_grad():
+        y4 = m(x)
+        y3 = m(x.flatten(1, 2))
+    assert y3.shape == (x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
+    torch.testing.assert_close(y3.view_as(y4), y4)

@@ -25,6 +25,9 @@ CASES = {
     "p3_m150": (1, 1, 150, 64, 64, True, False, "bf16", 3, True),
     "p3_rope": (1, 2, 4, 256, 64, True, True, "bf16", 3, True),
     "p3_rope_d128": (1, 1, 3, 128, 128, True, True, "fp16", 3, True),
+    "only_p3_tiny": (1, 1, 2, 128, 64, True, False, "bf16", 4, True),
+    "only_p3_w256": (1, 2, 4, 256, 64, True, False, "bf16", 4, True),
+    "only_p3_d128": (1, 2, 6, 210, 128, True, True, "bf16", 4, True),
     "fused_tiny": (1, 1, 2, 128, 64, True, False, "bf16", 3, False),
     "fused_mid": (2, 4, 32, 256, 64, True, False, "bf16", 3, False),
     "fused_d128": (1, 3, 20, 210, 128, True, True, "bf16", 3, False),
@@ -66,6 +69,8 @@ def run_case(name):
             flags |= _capi.FLAG_STOP_AFTER_P1
         elif stop == 2:
             flags |= _capi.FLAG_STOP_AFTER_P2
+        elif stop == 4:
+            flags |= _capi.FLAG_ONLY_P3
     d.flags, d.eps = flags, 1e-6
     d.q, d.k, d.v, d.out = _t5(tq), _t5(tk), _t5(tv), _t5(out)
     d.q_rope, d.k_rope = _t5(tqr), _t5(tkr)
@@ -77,7 +82,21 @@ def run_case(name):
     ws = torch.full((nbytes + 1024,), 0xFF, dtype=torch.uint8, device=dev)   # NaN-poisoned workspace
     base = (ws.data_ptr() + 1023) // 1024 * 1024
     shift = base - ws.data_ptr()
+    ws = ws
     d.workspace, d.workspace_bytes = base, nbytes
+    offS, offSt, offDen, offW, offC, ncols, wpad, Mp = [int(x) for x in lay]
+    G = B * H
+    f32 = torch.float32
+    qf, kf, vf = q.to(f32), k.to(f32), v.to(f32)
+    knum = kr.to(f32) if rope else kf
+    if stop == 4:   # readout only: fill S~ and den with oracle values
+        S_ref = oracle.blockmix_summaries(knum, vf).reshape(G, M, D * D)
+        St_ref = torch.einsum("ij,gjc->gic", W, S_ref).to(dtype)
+        ws[shift + offSt: shift + offSt + G * M * D * D * 2] = St_ref.contiguous().view(torch.uint8).flatten().to(dev)
+        nloc_ref = torch.einsum("bhjtd,bhjd->bhjt", qf, kf.sum(-2)).reshape(G, M, w)
+        den_ref = torch.zeros(G, M, wpad)
+        den_ref[:, :, :w] = torch.einsum("ij,gjt->git", W, nloc_ref) + 1e-6
+        ws[shift + offDen: shift + offDen + G * M * wpad * 4] = den_ref.contiguous().view(torch.uint8).flatten().to(dev)
     torch.cuda.synchronize()
     rc = L.mhla_fwd_blockmix(C.byref(d), torch.cuda.current_stream().cuda_stream)
     res = {"case": name, "rc": rc, "launches": L.mhla_last_launch_count()}
@@ -85,14 +104,16 @@ def run_case(name):
         res["err"] = L.mhla_strerror(rc).decode() + " / " + L.mhla_last_cuda_error().decode()
         return res
     torch.cuda.synchronize()
-    offS, offSt, offDen, offW, offC, ncols, wpad, Mp = [int(x) for x in lay]
-    G = B * H
     wsv = ws[shift:]
+    if stop == 4:
+        ref = oracle.blockmix_fwd(qf, kf, vf, W, eps=1e-6, normalize=normalize, q_rope=qr, k_rope=kr)
+        o = out.cpu().to(f32)
+        res["out_err"] = oracle.err_ratio(ref, o)
+        res["out_nan"] = int(torch.isnan(o).sum())
+        return res
+    Wp = wsv[offW:offW + M * Mp * 4].view(torch.float32).view(M, Mp).cpu()
+    res["Wp_err"] = oracle.err_ratio(W, Wp[:, :M])
     S_all = wsv[offS:offS + G * M * ncols * 4].view(torch.float32).view(G, M, ncols).cpu()
-    f32 = torch.float32
-    qf, kf, vf = q.to(f32), k.to(f32), v.to(f32)
-    knum = kr.to(f32) if rope else kf
-    qnum = qr.to(f32) if rope else qf
     S_ref = oracle.blockmix_summaries(knum, vf).reshape(G, M, D * D)
     res["S_err"] = oracle.err_ratio(S_ref, S_all[:, :, :D * D])
     res["S_nan"] = int(torch.isnan(S_all[:, :, :D * D]).sum())
