@@ -6,7 +6,10 @@
 // Work is cut into three kinds of items that flow through one TMA->smem ring, one tcgen05 issuer and one
 // epilogue warpgroup (see DESIGN.md "Kernel"):
 //   P1 (g, j)        S_j = K_j^T V_j  (+ ksum_j via an all-ones B operand, n_loc[j,t] = q_{j,t}.ksum_j)
-//   P2 (g, it, ic)   [S~ | den] rows it*128.., cols ic*128.. = mix . [S | n_loc]    (TF32 GEMM over blocks)
+//   P2 (g, it, ic)   [S~ | den] rows it*128.., cols ic*256.. = mix . [S | n_loc]    (GEMM over blocks; S is kept
+//                    in 16-bit, mix and n_loc are split hi+lo so the product carries ~16 mantissa bits.  A TF32
+//                    formulation is not possible: tcgen05 kind::tf32 returns zeros for an MN-major operand with
+//                    the plain 128B swizzle - see profiles/r01_microtest_umma_layouts.log)
 //   P3 (g, i)        O_i = (Q_i S~_i) / den_i
 // Items of different (b,h) groups g are interleaved in a fixed global order (P1(s), P3(s-lag3), P2(s-lag2))
 // so that the S / S~ / den workspace and the second read of Q are served from L2; cross-CTA dependencies
@@ -36,20 +39,20 @@ constexpr int kSmemAlloc = kSmemTotal + 1024;  // slack for manual 1024-byte ali
 
 struct alignas(64) BlockmixParams {
   CUtensorMap tmK, tmV, tmKn, tmQn, tmQr;   // rank-5 (d, w, M, H, B) views; Kn/Qn: un-roped (normaliser)
-  CUtensorMap tmSst;                        // S store   : (Dv, Dk, G*M)      fp32, box (32, Dk, 1)
-  CUtensorMap tmSld;                        // S load    : (ncols, M, G)      fp32, box (32, 32, 1)
-  CUtensorMap tmW;                          // mix       : (Mp, M)            fp32, box (32, 128)
-  CUtensorMap tmStst;                       // S~ store  : (D*D, M, G)        bf16/fp16, box (64, 128, 1)
-  CUtensorMap tmDen;                        // den store : (wpad, M, G)       fp32, box (32, 128, 1)
+  CUtensorMap tmSst;                        // S store   : (Dv, Dk, G*M)      16-bit, box (64, Dk, 1)
+  CUtensorMap tmSld;                        // S load    : (ncols, M, G)      16-bit, box (64, 64, 1)
+  CUtensorMap tmW;                          // mix hi/lo : (Mp, M, 2)         16-bit, box (64, 128, 1)
+  CUtensorMap tmStst;                       // S~ store  : (D*D, M, G)        16-bit, box (64, 128, 1)
+  CUtensorMap tmDen;                        // den store : (2*wpad, M, G)     fp32, box (32, 128, 1)  (hi | lo parts)
   CUtensorMap tmStld;                       // S~ load   : (Dv, Dk, G*M)      bf16/fp16, box (64, Dk, 1)
   CUtensorMap tmO;                          // out       : rank-5 like q
-  float* ws_S;                              // [G*M][ncols] fp32: S_j (Dk*Dv) | n_loc_j (wpad)
-  const float* den;                         // [G*M][wpad]
+  uint16_t* ws_S;                           // [G*M][ncols] 16-bit: S_j (Dk*Dv) | n_loc_j hi (wpad) | n_loc_j lo (wpad)
+  const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
   int G, H, M, w, TW, nsub;
   int ncols, wpad;
   int n2_rows, n2_cols, n2_scols;           // P2 tile grid; first n2_scols column tiles are S columns
-  int kslabs;                               // ceil(M / 32)
+  int kslabs;                               // ceil(M / 64)
   int normalize, ropenorm, is_fp16;
   int mode;                                 // 0: fused; 1/2/3: only that phase (unfused debugging path)
   int lag2, lag3;
@@ -222,13 +225,18 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (p.mode == 0) { spin_until(&p.counters[it.g], (uint32_t)p.M); fence_proxy_async_all(); }
           const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
           for (int slab = 0; slab < p.kslabs; ++slab) {
+            // stage X: mix hi | mix lo, [128 i][64 j] each; stage Y: [64 j][256 cols] as 4 tiles of 64 columns
             mbar_wait(&empty[r.stage], r.phase ^ 1);
             uint8_t* st = ring + r.stage * kStageBytes;
             mbar_arrive_expect_tx(&full[r.stage], 32768);
-            tma_load_2d(st, &p.tmW, &full[r.stage], slab * 32, ti * 128, kEvictLast);
+            tma_load_3d(st, &p.tmW, &full[r.stage], slab * 64, ti * 128, 0, kEvictLast);
+            tma_load_3d(st + 16384, &p.tmW, &full[r.stage], slab * 64, ti * 128, 1, kEvictLast);
+            r.advance();
+            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            st = ring + r.stage * kStageBytes;
+            mbar_arrive_expect_tx(&full[r.stage], 32768);
             for (int n4 = 0; n4 < 4; ++n4)
-              tma_load_3d(st + 16384 + n4 * 4096, &p.tmSld, &full[r.stage], tc * 128 + n4 * 32, slab * 32, it.g,
-                          kEvictNormal);
+              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.stage], tc * 256 + n4 * 64, slab * 64, it.g, kEvictNormal);
             r.advance();
           }
         } else {
@@ -277,7 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint64_t desc_ones = make_smem_desc(ones_addr, 256, 128, kSwizzleNone);
       const uint32_t idesc_p1 = make_idesc(fmt16, 1, 1, D, D);
       const uint32_t idesc_p1_ones = make_idesc(fmt16, 1, 1, D, 16);
-      const uint32_t idesc_p2 = make_idesc(2, 0, 1, 128, 128);
+      const uint32_t idesc_p2 = make_idesc(fmt16, 0, 1, 128, 256);
       const uint32_t idesc_p3 = make_idesc(fmt16, 0, 1, 128, D);
       while (sched.next(it)) {
         const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
@@ -330,14 +338,20 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         } else if (it.type == 2) {
           for (int slab = 0; slab < p.kslabs; ++slab) {
             mbar_wait(&full[r.stage], r.phase);
-            tc_fence_after();
             const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
-            const uint32_t b_addr = a_addr + 16384;
+            const int sa = r.stage;
+            r.advance();
+            mbar_wait(&full[r.stage], r.phase);
+            tc_fence_after();
+            const uint32_t b_addr = ring_addr + r.stage * kStageBytes;
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t da = make_smem_desc(a_addr + ks * 32, 0, 1024, kSwizzle128);         // K-major
-              const uint64_t db = make_smem_desc(b_addr + ks * 1024, 4096, 1024, kSwizzle128);    // MN-major
-              mma_tf32_ss(acc, da, db, idesc_p2, (slab | ks) != 0);
+              const uint64_t dhi = make_smem_desc(a_addr + ks * 32, 0, 1024, kSwizzle128);            // K-major
+              const uint64_t dlo = make_smem_desc(a_addr + 16384 + ks * 32, 0, 1024, kSwizzle128);
+              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 8192, 1024, kSwizzle128);        // MN-major
+              mma_f16_ss(acc, dhi, db, idesc_p2, (slab | ks) != 0);
+              mma_f16_ss(acc, dlo, db, idesc_p2, 1u);
             }
+            mma_commit(&empty[sa]);
             mma_commit(&empty[r.stage]);
             r.advance();
           }
@@ -399,6 +413,51 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       ++nstore;
     };
 
+    // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
+    auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        tmem_ld_x32(taddr + hh * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float a = __uint_as_float(v[2 * e]) * scale, bq = __uint_as_float(v[2 * e + 1]) * scale;
+          if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[hh * 16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
+          else pk[hh * 16 + e] = pack_bf16x2(a, bq);
+        }
+      }
+    };
+    // x = hi + lo with hi, lo in the 16-bit I/O type
+    auto split16 = [&](float x, uint16_t& hi, uint16_t& lo) {
+      if (p.is_fp16) {
+        const __half h = __float2half_rn(x);
+        const __half l = __float2half_rn(x - __half2float(h));
+        hi = __half_as_ushort(h); lo = __half_as_ushort(l);
+      } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+        hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(l);
+      }
+    };
+    // q_t . ksum over one 64-channel swizzled tile row
+    auto dot_row64 = [&](const uint8_t* tile, int rrow, const float* ks, float acc_n) -> float {
+      const uint4* rowp = reinterpret_cast<const uint4*>(tile + rrow * 128);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint4 u = rowp[c ^ (rrow & 7)];
+        const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          float2 f;
+          if (p.is_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
+          else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
+          acc_n = fmaf(f.x, ks[c * 8 + e * 2], acc_n);
+          acc_n = fmaf(f.y, ks[c * 8 + e * 2 + 1], acc_n);
+        }
+      }
+      return acc_n;
+    };
+
     while (sched.next(it)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
@@ -409,14 +468,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         // rows of S live in TMEM lanes: D == 128 -> lane = row; D == 64 (M=64 MMA) -> row r in lane 32*(r/16)+r%16
         const bool row_ok = (D == 128) || (lane < 16);
         const int row = (D == 128) ? et : (q4 * 16 + (lane & 15));
-        for (int c = 0; c < D / 32; ++c) {
-          tmem_ld_x32(acc + c * 32, v);
-          tmem_ld_wait();
+        for (int c = 0; c < D / 64; ++c) {
+          uint32_t pk[32];
+          load_pack64(acc + c * 64, 1.0f, pk);
           uint8_t* buf = staging_acquire();
-          if (row_ok) stage_row(buf, row, v);
+          if (row_ok) stage_row(buf, row, pk);
           staging_publish();
           if (et == 0) {
-            tma_store_3d(&p.tmSst, buf, c * 32, 0, it.g * p.M + j);
+            tma_store_3d(&p.tmSst, buf, c * 64, 0, it.g * p.M + j);
             tma_store_commit();
           }
         }
@@ -433,29 +492,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         r.advance(p.nsub * kvs);
         if (p.normalize) {
           named_bar_sync(3, kEpiThreads);  // ksum_s complete
-          float* nloc = p.ws_S + (size_t)(it.g * p.M + j) * p.ncols + D * D;
+          uint16_t* nloc = p.ws_S + (size_t)(it.g * p.M + j) * p.ncols + D * D;   // [hi: wpad][lo: wpad]
           if constexpr (D == 64) {
             mbar_wait(&full[r.stage], r.phase);
             const uint8_t* qs = ring + r.stage * kStageBytes;
             for (int t = et; t < p.wpad; t += kEpiThreads) {
-              float acc_n = 0.f;
-              if (t < p.nsub * p.TW) {
-                const uint4* rowp = reinterpret_cast<const uint4*>(qs + t * 128);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const uint4 u = rowp[c ^ (t & 7)];
-                  const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    float2 f;
-                    if (p.is_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
-                    else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
-                    acc_n = fmaf(f.x, ksum_s[c * 8 + e * 2], acc_n);
-                    acc_n = fmaf(f.y, ksum_s[c * 8 + e * 2 + 1], acc_n);
-                  }
-                }
-              }
-              nloc[t] = acc_n;
+              uint16_t hi, lo;
+              split16(dot_row64(qs, t, ksum_s, 0.f), hi, lo);
+              nloc[t] = hi;
+              nloc[p.wpad + t] = lo;
             }
             named_bar_sync(1, kEpiThreads);
             if (et == 0) mbar_arrive(&empty[r.stage]);
@@ -464,34 +509,19 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             for (int sub = 0; sub < p.nsub; ++sub) {
               mbar_wait(&full[r.stage], r.phase);
               const uint8_t* qs = ring + r.stage * kStageBytes;
-              const int t = sub * p.TW + et;
-              if (et < p.TW && t < p.wpad) {
-                float acc_n = 0.f;
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const uint4* rowp = reinterpret_cast<const uint4*>(qs + hh * 16384 + et * 128);
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) {
-                    const uint4 u = rowp[c ^ (et & 7)];
-                    const uint32_t uw[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                      float2 f;
-                      if (p.is_fp16) f = __half22float2(*reinterpret_cast<const __half2*>(&uw[e]));
-                      else f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&uw[e]));
-                      acc_n = fmaf(f.x, ksum_s[hh * 64 + c * 8 + e * 2], acc_n);
-                      acc_n = fmaf(f.y, ksum_s[hh * 64 + c * 8 + e * 2 + 1], acc_n);
-                    }
-                  }
-                }
-                nloc[t] = acc_n;
+              if (et < p.TW) {
+                const int t = sub * p.TW + et;
+                float a = dot_row64(qs, et, ksum_s, 0.f);
+                a = dot_row64(qs + 16384, et, ksum_s + 64, a);
+                uint16_t hi, lo;
+                split16(a, hi, lo);
+                nloc[t] = hi;
+                nloc[p.wpad + t] = lo;
               }
               named_bar_sync(1, kEpiThreads);
               if (et == 0) mbar_arrive(&empty[r.stage]);
               r.advance();
             }
-            // zero the padding columns [nsub*TW, wpad) if any (none when TW divides wpad)
-            for (int t = p.nsub * p.TW + et; t < p.wpad; t += kEpiThreads) nloc[t] = 0.f;
           }
         }
         if (p.mode == 0) {
@@ -508,43 +538,27 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         mbar_wait(&tfull[ab], aphase);
         tc_fence_after();
         if (tc < p.n2_scols) {
-          for (int hlf = 0; hlf < 2; ++hlf) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
-            tmem_ld_x32(acc + hlf * 64, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float a = __uint_as_float(v[2 * e]), bq = __uint_as_float(v[2 * e + 1]);
-              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[e] = *reinterpret_cast<uint32_t*>(&hv); }
-              else pk[e] = pack_bf16x2(a, bq);
-            }
-            tmem_ld_x32(acc + hlf * 64 + 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float a = __uint_as_float(v[2 * e]), bq = __uint_as_float(v[2 * e + 1]);
-              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
-              else pk[16 + e] = pack_bf16x2(a, bq);
-            }
+            load_pack64(acc + c * 64, 1.0f, pk);
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, pk);
             staging_publish();
             if (et == 0) {
-              tma_store_3d(&p.tmStst, buf, tc * 128 + hlf * 64, ti * 128, it.g);
+              tma_store_3d(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g);
               tma_store_commit();
             }
           }
         } else {
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 8; ++q) {
+            if ((tc - p.n2_scols) * 256 + q * 32 >= 2 * p.wpad) break;   // uniform: nothing left in this tile
             tmem_ld_x32(acc + q * 32, v);
             tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + p.eps);
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, v);
             staging_publish();
             if (et == 0) {
-              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 128 + q * 32, ti * 128, it.g);
+              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 256 + q * 32, ti * 128, it.g);
               tma_store_commit();
             }
           }
@@ -552,7 +566,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        r.advance(p.kslabs);
+        r.advance(2 * p.kslabs);
         if (p.mode == 0 && et == 0) {
           tma_store_wait_all<0>();
           fence_proxy_async_all();
@@ -561,39 +575,20 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         }
       } else {
         const int i = it.t;
-        float rden[2] = {1.f, 1.f};
-        if (p.normalize) {
-          // den was produced by other CTAs: the producer lane acquired the group counter before issuing this
-          // item's loads; read through L2 (.cg) after the accumulator barrier below orders us behind it.
-        }
         mbar_wait(&tfull[ab], aphase);
         tc_fence_after();
-        if (p.normalize) {
-          const float* dg = p.den + (size_t)(it.g * p.M + i) * p.wpad;
-          for (int sub = 0; sub < p.nsub; ++sub) {
-            const int t = sub * p.TW + et;
-            if (et < p.TW && t < p.w) rden[sub] = 1.0f / __ldcg(dg + t);
-          }
-        }
         for (int sub = 0; sub < p.nsub; ++sub) {
+          float rden = 1.f;
+          if (p.normalize) {
+            // den = mix.n_loc_hi + mix.n_loc_lo + eps, written by other CTAs (ordered behind the producer lane's
+            // acquire of the group counter by the barrier chain); read through L2
+            const float* dg = p.den + (size_t)(it.g * p.M + i) * (2 * p.wpad);
+            const int t = sub * p.TW + et;
+            if (et < p.TW && t < p.w) rden = 1.0f / (__ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps);
+          }
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
-            tmem_ld_x32(acc + sub * 128 + c * 64, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float a = __uint_as_float(v[2 * e]) * rden[sub], bq = __uint_as_float(v[2 * e + 1]) * rden[sub];
-              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[e] = *reinterpret_cast<uint32_t*>(&hv); }
-              else pk[e] = pack_bf16x2(a, bq);
-            }
-            tmem_ld_x32(acc + sub * 128 + c * 64 + 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float a = __uint_as_float(v[2 * e]) * rden[sub], bq = __uint_as_float(v[2 * e + 1]) * rden[sub];
-              if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
-              else pk[16 + e] = pack_bf16x2(a, bq);
-            }
+            load_pack64(acc + sub * 128 + c * 64, rden, pk);
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, pk);
             staging_publish();
@@ -620,16 +615,25 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// Tiny prologue: copy the mixing matrix into a 16-byte-pitched workspace buffer (optionally keeping only the
-// strictly-lower triangle, for the causal variant) and zero the dependency counters.
-__global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, float* __restrict__ out, int M, int Mp,
-                                int strict_lower, uint32_t* counters, int ncounters) {
+// Tiny prologue: split the fp32 mixing matrix into hi + lo 16-bit planes [2][M][Mp] (optionally keeping only the
+// strictly-lower triangle and folding a scale, for the causal variant) and zero the dependency counters.
+__global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, uint16_t* __restrict__ out, int M, int Mp,
+                                int strict_lower, float scale, int is_fp16, uint32_t* counters, int ncounters) {
   const int n = M * Mp;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int i = idx / Mp, j = idx % Mp;
     float v = 0.f;
-    if (j < M && (!strict_lower || j < i)) v = mix[(long long)i * ld + j];
-    out[idx] = v;
+    if (j < M && (!strict_lower || j < i)) v = mix[(long long)i * ld + j] * scale;
+    uint16_t hi, lo;
+    if (is_fp16) {
+      const __half h = __float2half_rn(v);
+      hi = __half_as_ushort(h); lo = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      hi = __bfloat16_as_ushort(h); lo = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
+    out[idx] = hi;
+    out[n + idx] = lo;
   }
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncounters; idx += gridDim.x * blockDim.x)
     counters[idx] = 0u;

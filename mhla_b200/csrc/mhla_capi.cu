@@ -94,18 +94,18 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->normalize = (d->flags & MHLA_FLAG_NORMALIZE) ? 1 : 0;
   pl->ropenorm = (pl->normalize && d->k_rope.ptr != nullptr) ? 1 : 0;
   pl->wpad = pl->normalize ? (pl->nsub * pl->TW) : 0;
-  pl->ncols = D * D + pl->wpad;
-  pl->Mp = (d->M + 3) / 4 * 4;
+  pl->ncols = D * D + 2 * pl->wpad;          // 16-bit elements: S_j | n_loc hi | n_loc lo
+  pl->Mp = (d->M + 7) / 8 * 8;
   pl->n2_rows = (d->M + 127) / 128;
-  pl->n2_scols = D * D / 128;
-  pl->n2_cols = pl->n2_scols + (pl->wpad + 127) / 128;
-  pl->kslabs = (d->M + 31) / 32;
+  pl->n2_scols = D * D / 256;
+  pl->n2_cols = pl->n2_scols + (2 * pl->wpad + 255) / 256;
+  pl->kslabs = (d->M + 63) / 64;
   size_t off = 0;
   const size_t GM = (size_t)pl->G * d->M;
-  pl->off_S = off;   off = align_up(off + GM * pl->ncols * 4, 1024);
+  pl->off_S = off;   off = align_up(off + GM * pl->ncols * 2, 1024);
   pl->off_St = off;  off = align_up(off + GM * D * D * 2, 1024);
-  pl->off_den = off; off = align_up(off + GM * (pl->wpad ? pl->wpad : 32) * 4, 1024);
-  pl->off_W = off;   off = align_up(off + (size_t)d->M * pl->Mp * 4, 1024);
+  pl->off_den = off; off = align_up(off + GM * (pl->wpad ? 2 * pl->wpad : 32) * 4, 1024);
+  pl->off_W = off;   off = align_up(off + (size_t)2 * d->M * pl->Mp * 2, 1024);
   pl->off_cnt = off; off = align_up(off + (size_t)2 * pl->G * 4, 1024);
   pl->total = off;
   return MHLA_OK;
@@ -141,14 +141,19 @@ struct CacheEntry {
 };
 std::mutex g_cache_mu;
 std::vector<CacheEntry> g_cache;
+struct CausalCacheEntry {
+  mhla_causal_desc key;
+  mhla::CausalParams params;
+};
+std::vector<CausalCacheEntry> g_causal_cache;
 
 int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, mhla::BlockmixParams* P) {
   const int D = d->D;
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
-  float* S = reinterpret_cast<float*>(ws + pl.off_S);
+  uint16_t* S = reinterpret_cast<uint16_t*>(ws + pl.off_S);
   void* St = ws + pl.off_St;
   float* den = reinterpret_cast<float*>(ws + pl.off_den);
-  float* Wp = reinterpret_cast<float*>(ws + pl.off_W);
+  uint16_t* Wp = reinterpret_cast<uint16_t*>(ws + pl.off_W);
   const uint64_t GM = (uint64_t)pl.G * d->M;
   const CUtensorMapDataType dt16 =
       d->dtype == MHLA_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -161,18 +166,18 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   if (!encode_map(&P->tmQr, spec_t5(d->q_rope.ptr ? d->q_rope : d->q, d, pl.TW))) return MHLA_ERR_CUDA;
   if (!encode_map(&P->tmO, spec_t5(d->out, d, pl.TW))) return MHLA_ERR_CUDA;
   {
-    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, S, {(uint64_t)D, (uint64_t)D, GM},
-              {(uint64_t)D * 4, (uint64_t)pl.ncols * 4}, {32, (uint32_t)D, 1}};
+    MapSpec s{dt16, 3, S, {(uint64_t)D, (uint64_t)D, GM}, {(uint64_t)D * 2, (uint64_t)pl.ncols * 2},
+              {64, (uint32_t)D, 1}};
     if (!encode_map(&P->tmSst, s)) return MHLA_ERR_CUDA;
   }
   {
-    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, S, {(uint64_t)pl.ncols, (uint64_t)d->M, (uint64_t)pl.G},
-              {(uint64_t)pl.ncols * 4, (uint64_t)d->M * pl.ncols * 4}, {32, 32, 1}};
+    MapSpec s{dt16, 3, S, {(uint64_t)pl.ncols, (uint64_t)d->M, (uint64_t)pl.G},
+              {(uint64_t)pl.ncols * 2, (uint64_t)d->M * pl.ncols * 2}, {64, 64, 1}};
     if (!encode_map(&P->tmSld, s)) return MHLA_ERR_CUDA;
   }
   {
-    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, Wp, {(uint64_t)pl.Mp, (uint64_t)d->M}, {(uint64_t)pl.Mp * 4},
-              {32, 128}};
+    MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)d->M, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)d->M * pl.Mp * 2},
+              {64, 128, 1}};
     if (!encode_map(&P->tmW, s)) return MHLA_ERR_CUDA;
   }
   {
@@ -181,7 +186,7 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
     if (!encode_map(&P->tmStst, s)) return MHLA_ERR_CUDA;
   }
   {
-    const uint64_t wp = pl.wpad ? pl.wpad : 32;
+    const uint64_t wp = pl.wpad ? 2 * pl.wpad : 32;
     MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, den, {wp, (uint64_t)d->M, (uint64_t)pl.G},
               {wp * 4, (uint64_t)d->M * wp * 4}, {32, 128, 1}};
     if (!encode_map(&P->tmDen, s)) return MHLA_ERR_CUDA;
@@ -295,8 +300,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
-  mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mix, (long long)d->mix_ld, reinterpret_cast<float*>(ws + pl.off_W),
-                                               d->M, pl.Mp, 0, P.counters, 2 * pl.G);
+  mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mix, (long long)d->mix_ld,
+                                               reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp, 0, 1.0f,
+                                               d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
   ++launches;
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
   if (d->flags & MHLA_FLAG_UNFUSED) {
@@ -323,11 +329,116 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }
 
-int mhla_fwd_causal(const mhla_causal_desc* desc, void* stream) {
+int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
+  mhla::CausalPlan pl;
+  int rc = mhla::plan_causal(d, &pl);
+  if (rc != MHLA_OK) return rc;
+  if (!d->q.ptr || !d->k.ptr || !d->v.ptr || !d->out.ptr || !d->mm) return MHLA_ERR_INVALID_ARGUMENT;
+  if (!d->workspace || d->workspace_bytes < pl.total) return MHLA_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(d->workspace) & 1023) != 0) return MHLA_ERR_ALIGNMENT;
+  const mhla_tensor4* ts[4] = {&d->q, &d->k, &d->v, &d->out};
+  for (const mhla_tensor4* t : ts) {
+    if ((reinterpret_cast<uintptr_t>(t->ptr) & 15) != 0) return MHLA_ERR_ALIGNMENT;
+    if (t->stride_b % 8 || t->stride_t % 8 || t->stride_h % 8) return MHLA_ERR_ALIGNMENT;
+  }
+  if (d->mm_ld < pl.n) return MHLA_ERR_INVALID_ARGUMENT;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (g_num_sms == 0) {
+    int dev = 0, major = 0, sms = 0;
+    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return MHLA_ERR_CUDA;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (major != 10) return MHLA_ERR_NO_DEVICE;
+    g_num_sms = sms;
+  }
+
+  mhla::CausalParams P;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    bool hit = false;
+    for (auto& e : g_causal_cache)
+      if (std::memcmp(&e.key, d, sizeof(*d)) == 0) { P = e.params; hit = true; break; }
+    if (!hit) {
+      std::memset(&P, 0, sizeof P);
+      const CUtensorMapDataType dt16 =
+          d->dtype == MHLA_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+      uint8_t* ws = static_cast<uint8_t*>(d->workspace);
+      void* S = ws + pl.off_S;
+      void* St = ws + pl.off_St;
+      void* Wp = ws + pl.off_W;
+      const uint64_t Gn = (uint64_t)pl.G * pl.n, KV = (uint64_t)d->K * d->V;
+      auto t4 = [&](const mhla_tensor4& t, int dim) {
+        // [B, T, H, dim] viewed as (dim, 64, n, H, B)
+        MapSpec s{};
+        s.dt = dt16; s.rank = 5; s.base = const_cast<void*>(t.ptr);
+        const uint64_t dims[5] = {(uint64_t)dim, 64, (uint64_t)pl.n, (uint64_t)d->H, (uint64_t)d->B};
+        const int64_t str[4] = {t.stride_t, t.stride_t * 64, t.stride_h, t.stride_b};
+        uint64_t prev = (uint64_t)dim * 2;
+        for (int i = 0; i < 5; ++i) s.dims[i] = dims[i];
+        for (int i = 0; i < 4; ++i) {
+          uint64_t bytes = (uint64_t)str[i] * 2;
+          if (dims[i + 1] == 1 || bytes == 0) bytes = prev;
+          s.strides[i] = bytes;
+          prev = bytes * dims[i + 1];
+        }
+        s.box[0] = 64; s.box[1] = 64; s.box[2] = s.box[3] = s.box[4] = 1;
+        return s;
+      };
+      if (!encode_map(&P.tmQ, t4(d->q, d->K))) return MHLA_ERR_CUDA;
+      if (!encode_map(&P.tmK, t4(d->k, d->K))) return MHLA_ERR_CUDA;
+      if (!encode_map(&P.tmV, t4(d->v, d->V))) return MHLA_ERR_CUDA;
+      if (!encode_map(&P.tmO, t4(d->out, d->V))) return MHLA_ERR_CUDA;
+      {
+        MapSpec s{dt16, 3, S, {(uint64_t)d->V, (uint64_t)d->K, Gn}, {(uint64_t)d->V * 2, KV * 2},
+                  {64, (uint32_t)d->K, 1}};
+        if (!encode_map(&P.tmSst, s)) return MHLA_ERR_CUDA;
+        s.base = St;
+        if (!encode_map(&P.tmStld, s)) return MHLA_ERR_CUDA;
+      }
+      {
+        MapSpec s{dt16, 3, S, {KV, (uint64_t)pl.n, (uint64_t)pl.G}, {KV * 2, (uint64_t)pl.n * KV * 2}, {64, 64, 1}};
+        if (!encode_map(&P.tmSld, s)) return MHLA_ERR_CUDA;
+        s.base = St; s.box[1] = 128;
+        if (!encode_map(&P.tmStst, s)) return MHLA_ERR_CUDA;
+      }
+      {
+        MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)pl.n, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)pl.n * pl.Mp * 2},
+                  {64, 128, 1}};
+        if (!encode_map(&P.tmW, s)) return MHLA_ERR_CUDA;
+      }
+      P.mm = d->mm; P.mm_ld = d->mm_ld;
+      P.counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+      P.G = pl.G; P.H = d->H; P.n = pl.n;
+      P.n2_rows = pl.n2_rows; P.n2_cols = pl.n2_cols; P.kslabs = pl.kslabs;
+      P.is_fp16 = d->dtype == MHLA_FP16; P.mode = 0; P.lag2 = 1; P.lag3 = 3;
+      P.scale = d->scale;
+      if (g_causal_cache.size() >= 32) g_causal_cache.erase(g_causal_cache.begin());
+      CausalCacheEntry e;
+      std::memcpy(&e.key, d, sizeof(*d));
+      e.params = P;
+      g_causal_cache.push_back(e);
+    }
+  }
+  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
-  int rc = mhla::causal_forward(desc, static_cast<cudaStream_t>(stream), &launches, &g_last_cuda_error);
-  if (rc == MHLA_OK) g_last_launches = launches;
-  return rc;
+  mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mm, (long long)d->mm_ld, reinterpret_cast<uint16_t*>(ws + pl.off_W),
+                                               pl.n, pl.Mp, 1, d->scale, d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
+  ++launches;
+  const int unfused = (d->flags & MHLA_FLAG_UNFUSED) ? 1 : 0;
+  rc = MHLA_ERR_UNSUPPORTED_SHAPE;
+#define MHLA_CAUSAL_CASE(KK, VV) \
+  if (d->K == KK && d->V == VV) rc = mhla::causal_launch<KK, VV>(P, pl, unfused, g_num_sms, stream, &launches);
+  MHLA_CAUSAL_CASE(64, 64)
+  MHLA_CAUSAL_CASE(64, 128)
+  MHLA_CAUSAL_CASE(128, 128)
+  MHLA_CAUSAL_CASE(128, 256)
+  MHLA_CAUSAL_CASE(64, 256)
+  MHLA_CAUSAL_CASE(128, 64)
+#undef MHLA_CAUSAL_CASE
+  if (rc != MHLA_OK) return rc;
+  if (!cuda_ok(cudaGetLastError(), "kernel launch")) return MHLA_ERR_CUDA;
+  g_last_launches = launches;
+  return MHLA_OK;
 }
 
 }  // extern "C"

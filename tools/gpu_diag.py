@@ -94,9 +94,9 @@ def run_case(name):
         St_ref = torch.einsum("ij,gjc->gic", W, S_ref).to(dtype)
         ws[shift + offSt: shift + offSt + G * M * D * D * 2] = St_ref.contiguous().view(torch.uint8).flatten().to(dev)
         nloc_ref = torch.einsum("bhjtd,bhjd->bhjt", qf, kf.sum(-2)).reshape(G, M, w)
-        den_ref = torch.zeros(G, M, wpad)
-        den_ref[:, :, :w] = torch.einsum("ij,gjt->git", W, nloc_ref) + 1e-6
-        ws[shift + offDen: shift + offDen + G * M * wpad * 4] = den_ref.contiguous().view(torch.uint8).flatten().to(dev)
+        den_ref = torch.zeros(G, M, 2 * wpad)
+        den_ref[:, :, :w] = torch.einsum("ij,gjt->git", W, nloc_ref)
+        ws[shift + offDen: shift + offDen + G * M * 2 * wpad * 4] = den_ref.contiguous().view(torch.uint8).flatten().to(dev)
     torch.cuda.synchronize()
     rc = L.mhla_fwd_blockmix(C.byref(d), torch.cuda.current_stream().cuda_stream)
     res = {"case": name, "rc": rc, "launches": L.mhla_last_launch_count()}
@@ -111,23 +111,23 @@ def run_case(name):
         res["out_err"] = oracle.err_ratio(ref, o)
         res["out_nan"] = int(torch.isnan(o).sum())
         return res
-    Wp = wsv[offW:offW + M * Mp * 4].view(torch.float32).view(M, Mp).cpu()
+    Wp = wsv[offW:offW + 2 * M * Mp * 2].view(dtype).view(2, M, Mp).cpu().float().sum(0)
     res["Wp_err"] = oracle.err_ratio(W, Wp[:, :M])
-    S_all = wsv[offS:offS + G * M * ncols * 4].view(torch.float32).view(G, M, ncols).cpu()
+    S_all = wsv[offS:offS + G * M * ncols * 2].view(dtype).view(G, M, ncols).cpu().float()
     S_ref = oracle.blockmix_summaries(knum, vf).reshape(G, M, D * D)
     res["S_err"] = oracle.err_ratio(S_ref, S_all[:, :, :D * D])
     res["S_nan"] = int(torch.isnan(S_all[:, :, :D * D]).sum())
     if normalize:
         nloc_ref = torch.einsum("bhjtd,bhjd->bhjt", qf, kf.sum(-2)).reshape(G, M, w)
-        res["nloc_err"] = oracle.err_ratio(nloc_ref, S_all[:, :, D * D:D * D + w])
+        res["nloc_err"] = oracle.err_ratio(nloc_ref, S_all[:, :, D * D:D * D + w] + S_all[:, :, D * D + wpad:D * D + wpad + w])
     if stop >= 2:
         St = wsv[offSt:offSt + G * M * D * D * 2].view(dtype).view(G, M, D * D).cpu().to(f32)
         St_ref = torch.einsum("ij,gjc->gic", W, S_ref)
         res["St_err"] = oracle.err_ratio(St_ref, St)
         if normalize:
-            den = wsv[offDen:offDen + G * M * wpad * 4].view(f32).view(G, M, wpad).cpu()
-            den_ref = torch.einsum("ij,gjt->git", W, nloc_ref) + 1e-6
-            res["den_err"] = oracle.err_ratio(den_ref, den[:, :, :w])
+            den = wsv[offDen:offDen + G * M * 2 * wpad * 4].view(f32).view(G, M, 2 * wpad).cpu()
+            den_ref = torch.einsum("ij,gjt->git", W, nloc_ref)
+            res["den_err"] = oracle.err_ratio(den_ref, den[:, :, :w] + den[:, :, wpad:wpad + w])
     if stop >= 3:
         ref = oracle.blockmix_fwd(qf, kf, vf, W, eps=1e-6, normalize=normalize, q_rope=qr, k_rope=kr)
         o = out.cpu().to(f32)
