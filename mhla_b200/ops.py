@@ -130,28 +130,36 @@ def _t4(t: torch.Tensor) -> _capi.Tensor4:
     return _capi.Tensor4(t.data_ptr(), sb, st, sh)
 
 
-def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None) -> torch.Tensor:
-    """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype."""
+def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
+                unfused: bool = False) -> torch.Tensor:
+    """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype.
+
+    T is zero-padded to a multiple of the chunk exactly as the reference does (naive.py:46-51); the pad is a host-side
+    copy that only happens for ragged T."""
     _require_cuda(q, k, v, mixing_matrix)
     in_dtype = q.dtype
     cdtype = in_dtype if in_dtype in _DT else torch.bfloat16
-    B, T, H, K = q.shape
+    B, T_in, H, K = q.shape
     V = v.shape[-1]
+    pad = (chunk_size - T_in % chunk_size) % chunk_size
+    T = T_in + pad
 
     def prep(t):
         t = t.to(cdtype) if t.dtype != cdtype else t
+        if pad:
+            t = torch.nn.functional.pad(t, (0, 0, 0, 0, 0, pad))
         return t if _tma_ok(t) else t.contiguous()
 
     q4, k4, v4 = prep(q), prep(k), prep(v)
     o4 = torch.empty((B, T, H, V), dtype=cdtype, device=q.device)
     Lm = mixing_matrix.shape[0]
     mm = mixing_matrix.detach().reshape(Lm, mixing_matrix.shape[1]).to(torch.float32).contiguous()
-    n = (T + chunk_size - 1) // chunk_size
+    n = T // chunk_size
     if n > Lm:
-        raise IndexError(f"mixing matrix is {Lm}x{Lm} but T={T} needs {n} chunks of {chunk_size}")
+        raise IndexError(f"mixing matrix is {Lm}x{Lm} but T={T_in} needs {n} chunks of {chunk_size}")
     d = _capi.CausalDesc()
     d.B, d.T, d.H, d.K, d.V = B, T, H, K, V
-    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], 0
+    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], (_capi.FLAG_UNFUSED if unfused else 0)
     d.scale = float(K ** -0.5 if scale is None else scale)
     d.q, d.k, d.v, d.out = _t4(q4), _t4(k4), _t4(v4), _t4(o4)
     d.mm, d.mm_ld, d.L = mm.data_ptr(), mm.stride(0), Lm
@@ -165,6 +173,8 @@ def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
         _capi.check(L.mhla_fwd_causal(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_causal")
     for t in (q4, k4, v4, mm, ws):
         t.record_stream(torch.cuda.current_stream())
+    if pad:
+        o4 = o4[:, :T_in]
     return o4 if in_dtype == cdtype else o4.to(in_dtype)
 
 
