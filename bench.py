@@ -81,7 +81,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.002)
 
     def summary(self):
         s = sorted(self.samples)
@@ -138,6 +138,7 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--unfused", action="store_true", help="debug: run the three phases as separate launches")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -167,7 +168,7 @@ def main():
     gathered = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=dev) if (args.gather and world > 1) else None
 
     def step():
-        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out)
+        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, unfused=args.unfused)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, out)
 

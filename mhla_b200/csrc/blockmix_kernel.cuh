@@ -23,7 +23,7 @@ namespace mhla {
 constexpr int kStageBytes = 32768;
 constexpr int kNumStages = 6;
 constexpr int kStagingBytes = 16384;  // x2 (double buffered epilogue staging, [128 rows][128 B] swizzle-128B)
-constexpr int kThreads = 256;         // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 4-7: epilogue
+constexpr int kThreads = 256;         // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 3: store/signal, 4-7: epilogue
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;         // two accumulator buffers of 256 columns
@@ -57,7 +57,22 @@ struct alignas(64) BlockmixParams {
   int mode;                                 // 0: fused; 1/2/3: only that phase (unfused debugging path)
   int lag2, lag3;
   float eps;
+  unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
 };
+
+// Event trace of CTA 0 (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
+__device__ __forceinline__ void trace_ev(const BlockmixParams& p, int role, uint32_t item, int slot) {
+  if (p.prof != nullptr && blockIdx.x == 0 && item < 256)
+    p.prof[(size_t)gridDim.x * 16 + ((size_t)role * 256 + item) * 4 + slot] = (unsigned long long)clock64();
+}
+
+// wait on an mbarrier and, when profiling, add the waited cycles to `acc`
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, bool on, long long& acc) {
+  if (!on) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
 
 struct Item {
   int type, g, t;
@@ -140,7 +155,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint64_t* empty = full + kNumStages;
   uint64_t* tfull = empty + kNumStages;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* sfull = tempty + 2;    // staging buffer written by the epilogue warps   (epilogue -> store warp)
+  uint64_t* sfree = sfull + 2;     // staging buffer read out by TMA                 (store warp -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
+  uint32_t* dep_count = tmem_slot + 1;   // dependencies confirmed by the dependency warp (warp 2), read by the producer
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -149,8 +167,11 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], kEpiThreads); mbar_init(&sfree[i], 1);
+    }
     fence_barrier_init();
+    *dep_count = 0;
     const CUtensorMap* maps = &p.tmK;
     for (int i = 0; i < 12; ++i) tma_prefetch_desc(maps + i);
   }
@@ -161,6 +182,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  grid_dependency_wait();   // PDL: everything above overlapped the tail of the prologue kernel (mix split, counters)
 
   Sched sched; sched.init(p);
   Item it;
@@ -169,14 +191,34 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // ============================================================ TMA producer (one lane)
     if (lane == 0) {
       Ring r;
+      uint32_t ndep = 0;   // dependency-bearing items seen so far
+      const bool prof_on = p.prof != nullptr;
+      long long w_empty = 0, w_dep = 0;
+      const long long t_begin = clock64();
+      uint32_t pitem = 0;
+      auto wait_dependency = [&]() {
+        // the dependency warp has already polled the group counter (global, ~1 us) - here it is a smem read
+        uint32_t spins = 0;
+        const long long t0 = clock64();
+        while (ld_acquire_cta_shared(dep_count) <= ndep) {
+          if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
+        }
+        ++ndep;
+        fence_proxy_async_all();
+        w_dep += clock64() - t0;
+        trace_ev(p, 0, pitem, 2);
+      };
       while (sched.next(it)) {
         const int b = it.g / p.H, h = it.g % p.H;
+        trace_ev(p, 0, pitem, 0);
+        if (p.prof != nullptr && blockIdx.x == 0 && pitem < 256)
+          p.prof[(size_t)gridDim.x * 16 + ((size_t)0 * 256 + pitem) * 4 + 3] = (unsigned long long)it.type;
         if (it.type == 1) {
           const int j = it.t;
           for (int sub = 0; sub < p.nsub; ++sub) {
             const int t0 = sub * p.TW;
             if constexpr (D == 64) {
-              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.stage * kStageBytes;
               mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
               tma_load_5d(st, &p.tmK, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
@@ -184,7 +226,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             } else {
               for (int kv = 0; kv < 2; ++kv) {
-                mbar_wait(&empty[r.stage], r.phase ^ 1);
+                mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
                 uint8_t* st = ring + r.stage * kStageBytes;
                 mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
                 const CUtensorMap* tm = kv ? &p.tmV : &p.tmK;
@@ -194,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               }
             }
             if (p.ropenorm) {
-              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.stage * kStageBytes;
               mbar_arrive_expect_tx(&full[r.stage], (D / 64) * tile_bytes);
               tma_load_5d(st, &p.tmKn, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
@@ -204,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           }
           if (p.normalize) {
             if constexpr (D == 64) {
-              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.stage * kStageBytes;
               mbar_arrive_expect_tx(&full[r.stage], p.nsub * tile_bytes);
               for (int sub = 0; sub < p.nsub; ++sub)
@@ -212,7 +254,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             } else {
               for (int sub = 0; sub < p.nsub; ++sub) {
-                mbar_wait(&empty[r.stage], r.phase ^ 1);
+                mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
                 uint8_t* st = ring + r.stage * kStageBytes;
                 mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
                 tma_load_5d(st, &p.tmQn, &full[r.stage], 0, sub * p.TW, j, h, b, kEvictLast);
@@ -222,17 +264,17 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
         } else if (it.type == 2) {
-          if (p.mode == 0) { spin_until(&p.counters[it.g], (uint32_t)p.M); fence_proxy_async_all(); }
+          if (p.mode == 0) wait_dependency();
           const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
           for (int slab = 0; slab < p.kslabs; ++slab) {
             // stage X: mix hi | mix lo, [128 i][64 j] each; stage Y: [64 j][256 cols] as 4 tiles of 64 columns
-            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
             uint8_t* st = ring + r.stage * kStageBytes;
             mbar_arrive_expect_tx(&full[r.stage], 32768);
             tma_load_3d(st, &p.tmW, &full[r.stage], slab * 64, ti * 128, 0, kEvictLast);
             tma_load_3d(st + 16384, &p.tmW, &full[r.stage], slab * 64, ti * 128, 1, kEvictLast);
             r.advance();
-            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
             st = ring + r.stage * kStageBytes;
             mbar_arrive_expect_tx(&full[r.stage], 32768);
             for (int n4 = 0; n4 < 4; ++n4)
@@ -240,15 +282,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             r.advance();
           }
         } else {
-          if (p.mode == 0) {
-            spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
-            fence_proxy_async_all();
-          }
+          if (p.mode == 0) wait_dependency();
           const int i = it.t;
           const CUtensorMap* tq = &p.tmQr;
           if constexpr (D == 64) {
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.stage * kStageBytes;
               mbar_arrive_expect_tx(&full[r.stage], tile_bytes + (sub == 0 ? 8192 : 0));
               tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
@@ -256,14 +295,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             }
           } else {
-            mbar_wait(&empty[r.stage], r.phase ^ 1);
+            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
             uint8_t* st = ring + r.stage * kStageBytes;
             mbar_arrive_expect_tx(&full[r.stage], 32768);
             tma_load_3d(st, &p.tmStld, &full[r.stage], 0, 0, it.g * p.M + i, kEvictFirst);
             tma_load_3d(st + 16384, &p.tmStld, &full[r.stage], 64, 0, it.g * p.M + i, kEvictFirst);
             r.advance();
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait(&empty[r.stage], r.phase ^ 1);
+              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
               st = ring + r.stage * kStageBytes;
               mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
               tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
@@ -272,6 +311,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
         }
+        trace_ev(p, 0, pitem, 1);
+        ++pitem;
+      }
+      if (prof_on) {
+        unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
+        pr[0] = (unsigned long long)w_empty; pr[1] = (unsigned long long)w_dep;
+        pr[2] = (unsigned long long)(clock64() - t_begin);
       }
     }
   } else if (warp == 1) {
@@ -279,6 +325,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     if (lane == 0) {
       Ring r;
       uint32_t nitem = 0;
+      const bool prof_on = p.prof != nullptr;
+      long long w_full = 0, w_tempty = 0;
       const uint32_t ring_addr = smem_u32(ring);
       const uint32_t ones_addr = smem_u32(ones);
       // all-ones B operand: no swizzle, MN-major, 2x2 core matrices of 128 B (LBO: K direction, SBO: N direction)
@@ -290,8 +338,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       while (sched.next(it)) {
         const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
         const uint32_t acc = tmem_base + ab * kAccCols;
-        mbar_wait(&tempty[ab], aphase ^ 1);
+        trace_ev(p, 1, nitem, 0);
+        mbar_wait_prof(&tempty[ab], aphase ^ 1, prof_on, w_tempty);
         tc_fence_after();
+        trace_ev(p, 1, nitem, 1);
         if (it.type == 1) {
           const int ksteps = p.TW / 16;
           const bool ones_here = p.normalize && !p.ropenorm;
@@ -299,15 +349,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint32_t a_addr, b_addr;
             Ring r0 = r;
             if constexpr (D == 64) {
-              mbar_wait(&full[r.stage], r.phase);
+              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
               a_addr = ring_addr + r.stage * kStageBytes;
               b_addr = a_addr + 16384;
               r.advance();
             } else {
-              mbar_wait(&full[r.stage], r.phase);
+              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
               a_addr = ring_addr + r.stage * kStageBytes;
               r.advance();
-              mbar_wait(&full[r.stage], r.phase);
+              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
               b_addr = ring_addr + r.stage * kStageBytes;
               r.advance();
             }
@@ -322,7 +372,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             mma_commit(&empty[r0.stage]);
             if constexpr (D == 128) mma_commit(&empty[r0.at(1).stage]);
             if (p.ropenorm) {
-              mbar_wait(&full[r.stage], r.phase);
+              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
               tc_fence_after();
               const uint32_t n_addr = ring_addr + r.stage * kStageBytes;
               for (int ks = 0; ks < ksteps; ++ks) {
@@ -337,11 +387,11 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (p.normalize) r.advance(D == 64 ? 1 : p.nsub);  // Q stages are consumed by the epilogue warps
         } else if (it.type == 2) {
           for (int slab = 0; slab < p.kslabs; ++slab) {
-            mbar_wait(&full[r.stage], r.phase);
+            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
             const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
             const int sa = r.stage;
             r.advance();
-            mbar_wait(&full[r.stage], r.phase);
+            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
             tc_fence_after();
             const uint32_t b_addr = ring_addr + r.stage * kStageBytes;
             for (int ks = 0; ks < 4; ++ks) {
@@ -360,12 +410,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           Ring r0 = r;
           uint32_t b_addr;
           if constexpr (D == 128) {
-            mbar_wait(&full[r.stage], r.phase);
+            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
             b_addr = ring_addr + r.stage * kStageBytes;
             r.advance();
           }
           for (int sub = 0; sub < p.nsub; ++sub) {
-            mbar_wait(&full[r.stage], r.phase);
+            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
             tc_fence_after();
             const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
             if constexpr (D == 64) { if (sub == 0) b_addr = a_addr + 16384; }
@@ -381,7 +431,25 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           for (int k = 0; k < ns; ++k) mma_commit(&empty[r0.at(k).stage]);
           mma_commit(&tfull[ab]);
         }
+        trace_ev(p, 1, nitem, 2);
         ++nitem;
+      }
+      if (prof_on) {
+        unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
+        pr[3] = (unsigned long long)w_full; pr[4] = (unsigned long long)w_tempty;
+      }
+    }
+  } else if (warp == 2) {
+    // ============================================================ dependency warp (one lane)
+    // Walks the same schedule ahead of the producer and polls the per-group counters in global memory, so that the
+    // producer lane never stalls on an L2 round trip for a dependency that is already satisfied.
+    if (lane == 0 && p.mode == 0) {
+      uint32_t n = 0;
+      while (sched.next(it)) {
+        if (it.type == 1) continue;
+        if (it.type == 2) spin_until(&p.counters[it.g], (uint32_t)p.M);
+        else spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
+        st_release_cta_shared(dep_count, ++n);
       }
     }
   } else if (warp >= 4) {
@@ -393,6 +461,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     uint32_t nitem = 0;
     uint32_t nstore = 0;                     // staging buffer toggles per TMA-store chunk
     uint32_t v[32];
+    const bool prof_on = p.prof != nullptr && et == 0;
+    long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0;
+    uint32_t ndep_e = 0;                     // dependency-bearing (P2/P3) items seen so far
 
     // write one [rows][128 B] chunk row into the swizzle-128B staging tile
     auto stage_row = [&](uint8_t* buf, int row, const uint32_t* w32) {
@@ -401,18 +472,16 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       for (int c = 0; c < 8; ++c)
         dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
     };
+    // staging hand-off with the store warp: chunk number nstore uses buffer nstore & 1
     auto staging_acquire = [&]() -> uint8_t* {
-      // the buffer we are about to overwrite was handed to TMA two chunks ago
-      if (et == 0) tma_store_wait_read<1>();
-      named_bar_sync(1, kEpiThreads);
+      mbar_wait_prof(&sfree[nstore & 1], ((nstore >> 1) & 1) ^ 1, prof_on, w_sfree);   // first use of each buffer passes immediately
       return staging + (nstore & 1) * kStagingBytes;
     };
     auto staging_publish = [&]() {
       fence_proxy_async_smem();
-      named_bar_sync(2, kEpiThreads);
+      mbar_arrive(&sfull[nstore & 1]);
       ++nstore;
     };
-
     // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
     auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
 #pragma unroll
@@ -461,53 +530,40 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     while (sched.next(it)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
+      const long long t_item = prof_on ? clock64() : 0;
+      if (et == 0) trace_ev(p, 2, nitem, 0);
       if (it.type == 1) {
-        const int j = it.t;
-        mbar_wait(&tfull[ab], aphase);
+        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         // rows of S live in TMEM lanes: D == 128 -> lane = row; D == 64 (M=64 MMA) -> row r in lane 32*(r/16)+r%16
         const bool row_ok = (D == 128) || (lane < 16);
         const int row = (D == 128) ? et : (q4 * 16 + (lane & 15));
-        for (int c = 0; c < D / 64; ++c) {
-          uint32_t pk[32];
-          load_pack64(acc + c * 64, 1.0f, pk);
-          uint8_t* buf = staging_acquire();
-          if (row_ok) stage_row(buf, row, pk);
-          staging_publish();
-          if (et == 0) {
-            tma_store_3d(&p.tmSst, buf, c * 64, 0, it.g * p.M + j);
-            tma_store_commit();
-          }
-        }
+        const int kvs = (D == 64 ? 1 : 2) + p.ropenorm;
+        r.advance(p.nsub * kvs);
         if (p.normalize) {
+          // ---- n_loc first: it frees the Q stage(s) of the ring early
           uint32_t ks;
           tmem_ld_x1(acc + kKsumCol, ks);
           tmem_ld_wait();
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[ab]);
-        const int kvs = (D == 64 ? 1 : 2) + p.ropenorm;
-        r.advance(p.nsub * kvs);
-        if (p.normalize) {
           named_bar_sync(3, kEpiThreads);  // ksum_s complete
-          uint16_t* nloc = p.ws_S + (size_t)(it.g * p.M + j) * p.ncols + D * D;   // [hi: wpad][lo: wpad]
+          uint16_t* nbuf = reinterpret_cast<uint16_t*>(staging_acquire());   // [hi: wpad][lo: wpad] -> one bulk store
           if constexpr (D == 64) {
-            mbar_wait(&full[r.stage], r.phase);
+            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_q);
             const uint8_t* qs = ring + r.stage * kStageBytes;
             for (int t = et; t < p.wpad; t += kEpiThreads) {
               uint16_t hi, lo;
               split16(dot_row64(qs, t, ksum_s, 0.f), hi, lo);
-              nloc[t] = hi;
-              nloc[p.wpad + t] = lo;
+              nbuf[t] = hi;
+              nbuf[p.wpad + t] = lo;
             }
             named_bar_sync(1, kEpiThreads);
             if (et == 0) mbar_arrive(&empty[r.stage]);
             r.advance();
           } else {
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait(&full[r.stage], r.phase);
+              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_q);
               const uint8_t* qs = ring + r.stage * kStageBytes;
               if (et < p.TW) {
                 const int t = sub * p.TW + et;
@@ -515,27 +571,30 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
                 a = dot_row64(qs + 16384, et, ksum_s + 64, a);
                 uint16_t hi, lo;
                 split16(a, hi, lo);
-                nloc[t] = hi;
-                nloc[p.wpad + t] = lo;
+                nbuf[t] = hi;
+                nbuf[p.wpad + t] = lo;
               }
               named_bar_sync(1, kEpiThreads);
               if (et == 0) mbar_arrive(&empty[r.stage]);
               r.advance();
             }
           }
+          staging_publish();
         }
-        if (p.mode == 0) {
-          named_bar_sync(2, kEpiThreads);  // every thread's n_loc stores are issued
-          if (et == 0) {
-            tma_store_wait_all<0>();
-            fence_proxy_async_all();
-            __threadfence();
-            red_release_gpu_add(&p.counters[it.g], 1u);
-          }
+        for (int c = 0; c < D / 64; ++c) {
+          uint32_t pk[32];
+          load_pack64(acc + c * 64, 1.0f, pk);
+          uint8_t* buf = staging_acquire();
+          if (row_ok) stage_row(buf, row, pk);
+          staging_publish();
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[ab]);
       } else if (it.type == 2) {
-        const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
-        mbar_wait(&tfull[ab], aphase);
+        const int tc = it.t % p.n2_cols;
+        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         if (tc < p.n2_scols) {
           for (int c = 0; c < 4; ++c) {
@@ -544,10 +603,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, pk);
             staging_publish();
-            if (et == 0) {
-              tma_store_3d(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g);
-              tma_store_commit();
-            }
           }
         } else {
           for (int q = 0; q < 8; ++q) {
@@ -557,46 +612,46 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, v);
             staging_publish();
-            if (et == 0) {
-              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 256 + q * 32, ti * 128, it.g);
-              tma_store_commit();
-            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
         r.advance(2 * p.kslabs);
-        if (p.mode == 0 && et == 0) {
-          tma_store_wait_all<0>();
-          fence_proxy_async_all();
-          __threadfence();
-          red_release_gpu_add(&p.counters[p.G + it.g], 1u);
-        }
       } else {
         const int i = it.t;
-        mbar_wait(&tfull[ab], aphase);
-        tc_fence_after();
-        for (int sub = 0; sub < p.nsub; ++sub) {
-          float rden = 1.f;
-          if (p.normalize) {
-            // den = mix.n_loc_hi + mix.n_loc_lo + eps, written by other CTAs (ordered behind the producer lane's
-            // acquire of the group counter by the barrier chain); read through L2
-            const float* dg = p.den + (size_t)(it.g * p.M + i) * (2 * p.wpad);
-            const int t = sub * p.TW + et;
-            if (et < p.TW && t < p.w) rden = 1.0f / (__ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps);
+        float dsum[2] = {1.f, 1.f};
+        if (p.normalize) {
+          // den = mix.n_loc_hi + mix.n_loc_lo + eps was written by other CTAs.  Once the dependency warp has confirmed
+          // this item's group (monotonic smem counter - NOT the ring barriers, whose phase may already have wrapped
+          // because P3 stages are recycled by the MMA warp alone), den is visible: fetch it through L2 now and let the
+          // latency overlap the wait for the accumulator.
+          if (p.mode == 0) {
+            uint32_t spins = 0;
+            while (ld_acquire_cta_shared(dep_count) <= ndep_e) {
+              if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: epilogue dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
+            }
           }
+          const float* dg = p.den + (size_t)(it.g * p.M + i) * (2 * p.wpad);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const int t = sub * p.TW + et;
+            if (sub < p.nsub && et < p.TW && t < p.w) dsum[sub] = __ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps;
+          }
+        }
+        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        if (et == 0) trace_ev(p, 2, nitem, 1);
+        tc_fence_after();
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          if (sub >= p.nsub) break;
+          const float rden = p.normalize ? 1.0f / dsum[sub] : 1.0f;
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
             load_pack64(acc + sub * 128 + c * 64, rden, pk);
             uint8_t* buf = staging_acquire();
             stage_row(buf, et, pk);
             staging_publish();
-            if (et == 0) {
-              const int b = it.g / p.H, h = it.g % p.H;
-              tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, i, h, b);
-              tma_store_commit();
-            }
           }
         }
         tc_fence_before();
@@ -604,9 +659,98 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(&tempty[ab]);
         r.advance(p3_stages<D>(p));
       }
+      if (it.type != 1) ++ndep_e;
+      if (et == 0) trace_ev(p, 2, nitem, 2);
+      if (prof_on) {
+        const long long dt = clock64() - t_item;
+        if (it.type == 1) t_p1 += dt; else if (it.type == 2) t_p2 += dt; else t_p3 += dt;
+      }
       ++nitem;
     }
-    if (et == 0) tma_store_wait_all<0>();
+    if (prof_on) {
+      unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
+      pr[5] = (unsigned long long)w_tfull; pr[6] = (unsigned long long)w_sfree; pr[7] = (unsigned long long)w_q;
+      pr[8] = (unsigned long long)t_p1; pr[9] = (unsigned long long)t_p2; pr[10] = (unsigned long long)t_p3;
+      pr[11] = nitem;
+    }
+  } else if (warp == 3) {
+    // ============================================================ store / signal warp (one lane)
+    // Issues every TMA store (so the bulk async-groups belong to this thread), recycles the staging buffers and
+    // publishes the per-group dependency counters once an item's stores have fully completed - none of this sits on
+    // the epilogue warps' critical path.
+    if (lane == 0) {
+      uint32_t k = 0, freed = 0;   // chunks issued / chunks whose staging buffer has been handed back
+      const bool prof_on = p.prof != nullptr;
+      long long w_sfull = 0, w_done = 0;
+      auto take = [&]() -> uint8_t* {
+        mbar_wait_prof(&sfull[k & 1], (k >> 1) & 1, prof_on, w_sfull);
+        return staging + (k & 1) * kStagingBytes;
+      };
+      auto issued = [&]() {
+        tma_store_commit();
+        ++k;
+        tma_store_wait_read<1>();              // everything but the newest group has been read out of smem
+        while (freed + 1 < k) { mbar_arrive(&sfree[freed & 1]); ++freed; }
+      };
+      uint32_t sitem = 0;
+      while (sched.next(it)) {
+        trace_ev(p, 3, sitem, 0);
+        if (it.type == 1) {
+          const int row = it.g * p.M + it.t;
+          if (p.normalize) {
+            uint8_t* buf = take();
+            bulk_store_1d(p.ws_S + (size_t)row * p.ncols + D * D, buf, (uint32_t)(4 * p.wpad));
+            issued();
+          }
+          for (int c = 0; c < D / 64; ++c) {
+            uint8_t* buf = take();
+            tma_store_3d(&p.tmSst, buf, c * 64, 0, row);
+            issued();
+          }
+        } else if (it.type == 2) {
+          const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+          if (tc < p.n2_scols) {
+            for (int c = 0; c < 4; ++c) {
+              uint8_t* buf = take();
+              tma_store_3d(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g);
+              issued();
+            }
+          } else {
+            for (int q = 0; q < 8; ++q) {
+              if ((tc - p.n2_scols) * 256 + q * 32 >= 2 * p.wpad) break;
+              uint8_t* buf = take();
+              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 256 + q * 32, ti * 128, it.g);
+              issued();
+            }
+          }
+        } else {
+          const int b = it.g / p.H, h = it.g % p.H;
+          for (int sub = 0; sub < p.nsub; ++sub)
+            for (int c = 0; c < D / 64; ++c) {
+              uint8_t* buf = take();
+              tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, it.t, h, b);
+              issued();
+            }
+        }
+        trace_ev(p, 3, sitem, 1);
+        if (p.mode == 0 && it.type != 3) {
+          const long long t0 = prof_on ? clock64() : 0;
+          tma_store_wait_all<0>();             // the item's S / n_loc / S~ / den bytes are in global memory
+          if (prof_on) w_done += clock64() - t0;
+          while (freed < k) { mbar_arrive(&sfree[freed & 1]); ++freed; }
+          fence_proxy_async_all();
+          __threadfence();
+          red_release_gpu_add(&p.counters[(it.type == 1 ? 0 : p.G) + it.g], 1u);
+        }
+        trace_ev(p, 3, sitem, 2);
+        ++sitem;
+      }
+      tma_store_wait_all<0>();
+      if (prof_on) {
+        unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
+        pr[12] = (unsigned long long)w_sfull; pr[13] = (unsigned long long)w_done;
+      }
+    }
   }
 
   // ---------------------------------------------------------------- teardown
@@ -619,6 +763,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 // strictly-lower triangle and folding a scale, for the causal variant) and zero the dependency counters.
 __global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, uint16_t* __restrict__ out, int M, int Mp,
                                 int strict_lower, float scale, int is_fp16, uint32_t* counters, int ncounters) {
+  grid_launch_dependents();   // the main kernel may start its prologue now; it waits (griddepcontrol.wait) for our results
   const int n = M * Mp;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int i = idx / Mp, j = idx % Mp;

@@ -2,6 +2,7 @@
 // (driver entry point resolved at run time - no link-time dependency on libcuda) and kernel launches.
 // See include/mhla_b200.h for the contract.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -210,6 +211,7 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
 }
 
 int g_num_sms = 0;
+unsigned long long* g_prof_buffer = nullptr;   // debug: per-CTA role counters (mhla_debug_set_profile_buffer)
 bool g_attr_set64 = false, g_attr_set128 = false;
 
 }  // namespace
@@ -289,6 +291,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     }
   }
 
+  P.prof = g_prof_buffer;
+  if (const char* e = std::getenv("MHLA_LAG2")) P.lag2 = std::atoi(e);   // tuning knobs (schedule distance, in groups,
+  if (const char* e = std::getenv("MHLA_LAG3")) P.lag3 = std::atoi(e);   // between the phases of one (b,h) group)
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
   bool& attr = d->D == 64 ? g_attr_set64 : g_attr_set128;
   if (!attr) {
@@ -319,13 +324,27 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     P.mode = 0;
     const long long items = (long long)pl.G * (n1 + n2 + n3);
     const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-    kern<<<grid, mhla::kThreads, mhla::kSmemAlloc, stream>>>(P);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(mhla::kThreads);
+    cfg.dynamicSmemBytes = mhla::kSmemAlloc;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the mix-split kernel
+    attrs[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    if (!cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx")) return MHLA_ERR_CUDA;
     ++launches;
   }
   if (!cuda_ok(cudaGetLastError(), "kernel launch")) return MHLA_ERR_CUDA;
   g_last_launches = launches;
   return MHLA_OK;
 }
+
+/* Debug hook (not part of the stable ABI): device buffer of [#SMs][16] uint64 that receives per-CTA wait-cycle counters
+ * of the blockmix kernel's warp roles; NULL switches the instrumentation off. */
+void mhla_debug_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }
 
