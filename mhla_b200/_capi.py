@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmhla_b200.so")
+LIB_PATH = os.environ.get("MHLA_B200_LIB") or os.path.join(_HERE, "libmhla_b200.so")   # env override: A/B builds while tuning
 
 MHLA_BF16, MHLA_FP16 = 0, 1
 FLAG_NORMALIZE = 1 << 0

@@ -23,7 +23,8 @@ namespace mhla {
 constexpr int kStageBytes = 32768;
 constexpr int kNumStages = 6;
 constexpr int kStagingBytes = 16384;  // x2 (double buffered epilogue staging, [128 rows][128 B] swizzle-128B)
-constexpr int kThreads = 256;         // warp 0: TMA producer, 1: MMA issuer, 2: TMEM allocator, 3: store/signal, 4-7: epilogue
+constexpr int kThreads = 384;         // warp 0: TMA producer, 1: MMA issuer, 2: dependency poller (+TMEM alloc),
+                                      // 3: store/signal, 4-7: epilogue warpgroup 0 (even items), 8-11: warpgroup 1 (odd items)
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;         // two accumulator buffers of 256 columns
@@ -33,7 +34,7 @@ constexpr int kSmemRing = 0;
 constexpr int kSmemStaging = kStageBytes * kNumStages;
 constexpr int kSmemOnes = kSmemStaging + 2 * kStagingBytes;
 constexpr int kSmemKsum = kSmemOnes + 512;
-constexpr int kSmemBars = kSmemKsum + 512;
+constexpr int kSmemBars = kSmemKsum + 1024;   // ksum: 128 floats per epilogue warpgroup
 constexpr int kSmemTotal = kSmemBars + 256;
 constexpr int kSmemAlloc = kSmemTotal + 1024;  // slack for manual 1024-byte alignment
 
@@ -58,6 +59,8 @@ struct alignas(64) BlockmixParams {
   int lag2, lag3;
   float eps;
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
+  int dep_mode;                             // tuning: 0 = 32-lane dependency warp, 1 = single polling lane
+  int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
 };
 
 // Event trace of CTA 0 (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < kNumStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], kEpiThreads); mbar_init(&sfree[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], 4); mbar_init(&sfree[i], 1);
     }
     fence_barrier_init();
     *dep_count = 0;
@@ -335,6 +338,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint32_t idesc_p1_ones = make_idesc(fmt16, 1, 1, D, 16);
       const uint32_t idesc_p2 = make_idesc(fmt16, 0, 1, 128, 256);
       const uint32_t idesc_p3 = make_idesc(fmt16, 0, 1, 128, D);
+      // This lane's instruction stream is latency-bound (one thread, dependent integer ops), so the issue loops carry
+      // as few instructions as possible: descriptors are built once per stage and advanced by adding to the 14-bit
+      // start-address field ((bytes >> 4); no carry can leave the field for addresses < 256 KB).
+      const uint64_t tmpl_mn16k = make_smem_desc(0, 16384, 1024, kSwizzle128);   // MN-major, 64-channel tiles 16 KB apart
+      const uint64_t tmpl_mn8k = make_smem_desc(0, 8192, 1024, kSwizzle128);     // MN-major, tiles 8 KB apart (P2 B operand)
+      const uint64_t tmpl_k = make_smem_desc(0, 0, 1024, kSwizzle128);           // K-major
+      auto dsc = [](uint64_t tmpl, uint32_t saddr) -> uint64_t { return tmpl | (uint64_t)((saddr & 0x3FFFF) >> 4); };
       while (sched.next(it)) {
         const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
         const uint32_t acc = tmem_base + ab * kAccCols;
@@ -344,7 +354,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         trace_ev(p, 1, nitem, 1);
         if (it.type == 1) {
           const int ksteps = p.TW / 16;
-          const bool ones_here = p.normalize && !p.ropenorm;
           for (int sub = 0; sub < p.nsub; ++sub) {
             uint32_t a_addr, b_addr;
             Ring r0 = r;
@@ -362,19 +371,35 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             }
             tc_fence_after();
-            for (int ks = 0; ks < ksteps; ++ks) {
-              // MN-major, 128B swizzle: 8 token rows per atom (SBO = 1024 B), 64 channels per atom (LBO = 16 KB)
-              const uint64_t da = make_smem_desc(a_addr + ks * 2048, 16384, 1024, kSwizzle128);
-              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 16384, 1024, kSwizzle128);
-              mma_f16_ss(acc, da, db, idesc_p1, (sub | ks) != 0);
-              if (ones_here) mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
+            // MN-major, 128B swizzle: 8 token rows per atom (SBO = 1024 B), 64 channels per atom (LBO = 16 KB);
+            // one k-step = 16 tokens = 2048 B = 128 descriptor units
+            const uint64_t da0 = dsc(tmpl_mn16k, a_addr), db0 = dsc(tmpl_mn16k, b_addr);
+            const uint32_t first = sub != 0;
+            // ksum accumulates K^T . 1 with the un-roped K: the same tile as A (variant A) or its own stage (variant B with
+            // the normaliser).  The narrow N=16 MMAs are always interleaved with the main ones - a back-to-back run of
+            // them produced wrong sums on B200 (profiles/r01_bringup_notes.md).
+            if (p.normalize && !p.ropenorm) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                if (ks < ksteps) {
+                  mma_f16_ss(acc, da0 + ks * 128, db0 + ks * 128, idesc_p1, ks ? 1u : first);
+                  mma_f16_ss(acc + kKsumCol, da0 + ks * 128, desc_ones, idesc_p1_ones, ks ? 1u : first);
+                }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks)
+                if (ks < ksteps) mma_f16_ss(acc, da0 + ks * 128, db0 + ks * 128, idesc_p1, ks ? 1u : first);
             }
             mma_commit(&empty[r0.stage]);
             if constexpr (D == 128) mma_commit(&empty[r0.at(1).stage]);
             if (p.ropenorm) {
+              // ksum of the un-roped K (variant B with the normaliser) from its own stage.  NOTE: issued as a plain
+              // (not unrolled, descriptor rebuilt per step) loop on purpose - a full-speed back-to-back run of these
+              // narrow N=16 accumulating MMAs gave wrong sums on B200 (profiles/r01_bringup_notes.md).
               mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
               tc_fence_after();
               const uint32_t n_addr = ring_addr + r.stage * kStageBytes;
+#pragma unroll 1
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t da = make_smem_desc(n_addr + ks * 2048, 16384, 1024, kSwizzle128);
                 mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
@@ -393,13 +418,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             r.advance();
             mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
             tc_fence_after();
-            const uint32_t b_addr = ring_addr + r.stage * kStageBytes;
+            const uint64_t dhi0 = dsc(tmpl_k, a_addr), dlo0 = dsc(tmpl_k, a_addr + 16384);   // K-major: 32 B per k-step
+            const uint64_t db0 = dsc(tmpl_mn8k, ring_addr + r.stage * kStageBytes);           // MN-major: 2048 B per k-step
+            const uint32_t first = slab != 0;
+#pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint64_t dhi = make_smem_desc(a_addr + ks * 32, 0, 1024, kSwizzle128);            // K-major
-              const uint64_t dlo = make_smem_desc(a_addr + 16384 + ks * 32, 0, 1024, kSwizzle128);
-              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 8192, 1024, kSwizzle128);        // MN-major
-              mma_f16_ss(acc, dhi, db, idesc_p2, (slab | ks) != 0);
-              mma_f16_ss(acc, dlo, db, idesc_p2, 1u);
+              mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
+              mma_f16_ss(acc, dlo0 + ks * 2, db0 + ks * 128, idesc_p2, 1u);
             }
             mma_commit(&empty[sa]);
             mma_commit(&empty[r.stage]);
@@ -419,12 +444,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             tc_fence_after();
             const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
             if constexpr (D == 64) { if (sub == 0) b_addr = a_addr + 16384; }
-            for (int ks = 0; ks < D / 16; ++ks) {
-              const uint32_t a_off = (ks >> 2) * 16384 + (ks & 3) * 32;  // K-major: 4 k-steps per 64-channel tile
-              const uint64_t da = make_smem_desc(a_addr + a_off, 0, 1024, kSwizzle128);
-              const uint64_t db = make_smem_desc(b_addr + ks * 2048, 16384, 1024, kSwizzle128);
-              mma_f16_ss(acc + sub * 128, da, db, idesc_p3, ks != 0);
-            }
+            const uint64_t da0 = dsc(tmpl_k, a_addr), db0 = dsc(tmpl_mn16k, b_addr);
+#pragma unroll
+            for (int ks = 0; ks < D / 16; ++ks)   // K-major A: 4 k-steps (32 B each) per 64-channel tile, tiles 16 KB apart
+              mma_f16_ss(acc + sub * 128, da0 + (ks >> 2) * 1024 + (ks & 3) * 2, db0 + ks * 128, idesc_p3, ks != 0);
             r.advance();
           }
           const int ns = p3_stages<D>(p);
@@ -440,28 +463,73 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
     }
   } else if (warp == 2) {
-    // ============================================================ dependency warp (one lane)
-    // Walks the same schedule ahead of the producer and polls the per-group counters in global memory, so that the
-    // producer lane never stalls on an L2 round trip for a dependency that is already satisfied.
-    if (lane == 0 && p.mode == 0) {
-      uint32_t n = 0;
-      while (sched.next(it)) {
-        if (it.type == 1) continue;
-        if (it.type == 2) spin_until(&p.counters[it.g], (uint32_t)p.M);
-        else spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
-        st_release_cta_shared(dep_count, ++n);
+    // ============================================================ dependency warp (32 lanes)
+    // Polls the per-group counters in global memory for the producer.  An L2 round trip under load costs microseconds,
+    // so the 32 lanes watch the next 32 dependency-bearing items concurrently (lane L owns dependencies L, L+32, ...)
+    // and the confirmed prefix is published through a monotonic counter in shared memory.
+    if (p.mode == 0 && p.dep_mode == 1) {
+      if (lane == 0) {
+        uint32_t n = 0;
+        while (sched.next(it)) {
+          if (it.type == 1) continue;
+          if (it.type == 2) spin_until(&p.counters[it.g], (uint32_t)p.M);
+          else spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
+          st_release_cta_shared(dep_count, ++n);
+        }
+      }
+    } else if (p.mode == 0) {
+      uint32_t n = 0;            // dependencies confirmed so far (warp-uniform)
+      uint32_t my_idx = lane;    // the dependency this lane is watching
+      uint32_t seen = 0;         // dependency-bearing items this lane's private schedule walk has passed
+      const uint32_t* my_ptr = nullptr;
+      uint32_t my_target = 0;
+      bool have = false;
+      auto advance_to = [&](uint32_t idx) {
+        have = false;
+        while (sched.next(it)) {
+          if (it.type == 1) continue;
+          if (seen++ == idx) {
+            my_ptr = (it.type == 2) ? &p.counters[it.g] : &p.counters[p.G + it.g];
+            my_target = (it.type == 2) ? (uint32_t)p.M : (uint32_t)(p.n2_rows * p.n2_cols);
+            have = true;
+            break;
+          }
+        }
+      };
+      advance_to(my_idx);
+      uint32_t idle = 0;
+      while (true) {
+        const bool ok = have ? (ld_acquire_gpu(my_ptr) >= my_target) : true;   // past-the-end lanes never block
+        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
+        const uint32_t any_have = __ballot_sync(0xffffffffu, have);
+        const uint32_t rot = n & 31;
+        const uint32_t rmask = rot ? ((mask >> rot) | (mask << (32 - rot))) : mask;
+        const uint32_t cnt = (rmask == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~rmask) - 1);
+        if (cnt > 0) {
+          if (lane == 0) st_release_cta_shared(dep_count, n + cnt);
+          if (((lane - rot) & 31) < cnt && have) { my_idx += 32; advance_to(my_idx); }
+          n += cnt;
+          idle = 0;
+        } else {
+          __nanosleep(128);
+          if (++idle > (1u << 22)) { if (lane == 0) printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+        }
+        if (any_have == 0) break;
       }
     }
   } else if (warp >= 4) {
     // ============================================================ epilogue warpgroup (TMEM -> regs -> smem -> TMA)
     const int q4 = warp & 3;                 // TMEM sub-partition (lanes 32*q4 .. 32*q4+31)
-    const int et = threadIdx.x - 128;        // 0..127
+    const int wg = (warp - 4) >> 2;          // epilogue warpgroup: handles the items whose accumulator buffer is `wg`
+    const int et = threadIdx.x - 128 - wg * kEpiThreads;   // 0..127 within the warpgroup
+    ksum_s += wg * 128;
+    const uint32_t bar_base = 1 + wg * 4;    // named barrier ids of this warpgroup
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     Ring r;
     uint32_t nitem = 0;
     uint32_t nstore = 0;                     // staging buffer toggles per TMA-store chunk
     uint32_t v[32];
-    const bool prof_on = p.prof != nullptr && et == 0;
+    const bool prof_on = p.prof != nullptr && et == 0 && wg == 0;
     long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0;
     uint32_t ndep_e = 0;                     // dependency-bearing (P2/P3) items seen so far
 
@@ -472,27 +540,32 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       for (int c = 0; c < 8; ++c)
         dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
     };
-    // staging hand-off with the store warp: chunk number nstore uses buffer nstore & 1
+    // staging hand-off with the store warp: warpgroup `wg` owns staging buffer `wg`; nstore counts its chunks
     auto staging_acquire = [&]() -> uint8_t* {
-      mbar_wait_prof(&sfree[nstore & 1], ((nstore >> 1) & 1) ^ 1, prof_on, w_sfree);   // first use of each buffer passes immediately
-      return staging + (nstore & 1) * kStagingBytes;
+      mbar_wait_prof(&sfree[wg], (nstore & 1) ^ 1, prof_on, w_sfree);   // first use passes immediately
+      return staging + wg * kStagingBytes;
     };
     auto staging_publish = [&]() {
-      fence_proxy_async_smem();
-      mbar_arrive(&sfull[nstore & 1]);
+      fence_proxy_async_smem();                 // my rows -> visible to the async proxy (TMA)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sfull[wg]);   // one arrival per epilogue warp
       ++nstore;
     };
     // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
     auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
+      uint32_t v2[32];
+      tmem_ld_x32(taddr, v);
+      tmem_ld_x32(taddr + 32, v2);
+      tmem_ld_wait();
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        tmem_ld_x32(taddr + hh * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float a = __uint_as_float(v[2 * e]) * scale, bq = __uint_as_float(v[2 * e + 1]) * scale;
-          if (p.is_fp16) { __half2 hv = __floats2half2_rn(a, bq); pk[hh * 16 + e] = *reinterpret_cast<uint32_t*>(&hv); }
-          else pk[hh * 16 + e] = pack_bf16x2(a, bq);
+      for (int e = 0; e < 16; ++e) {
+        const float a = __uint_as_float(v[2 * e]) * scale, bq = __uint_as_float(v[2 * e + 1]) * scale;
+        const float c2 = __uint_as_float(v2[2 * e]) * scale, d2 = __uint_as_float(v2[2 * e + 1]) * scale;
+        if (p.is_fp16) {
+          __half2 h0 = __floats2half2_rn(a, bq), h1 = __floats2half2_rn(c2, d2);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h0); pk[16 + e] = *reinterpret_cast<uint32_t*>(&h1);
+        } else {
+          pk[e] = pack_bf16x2(a, bq); pk[16 + e] = pack_bf16x2(c2, d2);
         }
       }
     };
@@ -530,6 +603,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     while (sched.next(it)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
+      if ((int)ab != wg) {   // the other warpgroup's item: only keep the ring / dependency bookkeeping in step
+        r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? 2 * p.kslabs : p3_stages<D>(p)));
+        if (it.type != 1) ++ndep_e;
+        ++nitem;
+        continue;
+      }
       const long long t_item = prof_on ? clock64() : 0;
       if (et == 0) trace_ev(p, 2, nitem, 0);
       if (it.type == 1) {
@@ -547,7 +626,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           tmem_ld_x1(acc + kKsumCol, ks);
           tmem_ld_wait();
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
-          named_bar_sync(3, kEpiThreads);  // ksum_s complete
+          named_bar_sync(bar_base + 2, kEpiThreads);  // ksum_s complete
           uint16_t* nbuf = reinterpret_cast<uint16_t*>(staging_acquire());   // [hi: wpad][lo: wpad] -> one bulk store
           if constexpr (D == 64) {
             mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_q);
@@ -558,7 +637,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               nbuf[t] = hi;
               nbuf[p.wpad + t] = lo;
             }
-            named_bar_sync(1, kEpiThreads);
+            named_bar_sync(bar_base, kEpiThreads);
             if (et == 0) mbar_arrive(&empty[r.stage]);
             r.advance();
           } else {
@@ -574,7 +653,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
                 nbuf[t] = hi;
                 nbuf[p.wpad + t] = lo;
               }
-              named_bar_sync(1, kEpiThreads);
+              named_bar_sync(bar_base, kEpiThreads);
               if (et == 0) mbar_arrive(&empty[r.stage]);
               r.advance();
             }
@@ -627,10 +706,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           // because P3 stages are recycled by the MMA warp alone), den is visible: fetch it through L2 now and let the
           // latency overlap the wait for the accumulator.
           if (p.mode == 0) {
-            uint32_t spins = 0;
-            while (ld_acquire_cta_shared(dep_count) <= ndep_e) {
-              if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: epilogue dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
+            if (lane == 0) {     // one poller per warp: 128 threads spinning on one smem word would starve the banks
+              uint32_t spins = 0;
+              while (ld_acquire_cta_shared(dep_count) <= ndep_e) {
+                __nanosleep(32);
+                if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: epilogue dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
+              }
             }
+            __syncwarp();
           }
           const float* dg = p.den + (size_t)(it.g * p.M + i) * (2 * p.wpad);
 #pragma unroll
@@ -679,21 +762,53 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // publishes the per-group dependency counters once an item's stores have fully completed - none of this sits on
     // the epilogue warps' critical path.
     if (lane == 0) {
-      uint32_t k = 0, freed = 0;   // chunks issued / chunks whose staging buffer has been handed back
+      uint32_t k = 0;              // bulk groups committed so far
       const bool prof_on = p.prof != nullptr;
       long long w_sfull = 0, w_done = 0;
+      // Completion signals are deferred instead of draining the store queue after every item: bulk groups retire in
+      // order, so once kSigLag younger groups have been committed, `wait_group kSigLag` (normally already satisfied)
+      // proves the item's bytes are in global memory.  Whenever the warp would idle it flushes everything pending, so
+      // a signal never waits on work that (transitively) depends on it.
+      constexpr int kSigLag = 1, kMaxPending = 8;
+      uint32_t* pend_ptr[kMaxPending] = {};
+      uint32_t pend_seq[kMaxPending] = {};
+      int pend_head = 0, pend_n = 0;
+      auto fire = [&](uint32_t upto_seq) {     // publish every pending signal whose last group index is <= upto_seq
+        bool fenced = false;
+        while (pend_n > 0 && pend_seq[pend_head] <= upto_seq) {
+          if (!fenced) { fence_proxy_async_all(); __threadfence(); fenced = true; }
+          red_release_gpu_add(pend_ptr[pend_head], 1u);
+          pend_head = (pend_head + 1) % kMaxPending;
+          --pend_n;
+        }
+      };
+      uint32_t kw[2] = {0, 0};   // chunks taken from each warpgroup's staging buffer
+      int cur = 0;               // warpgroup (= item parity) of the item being stored
+      auto drain_all = [&]() {
+        const long long t0 = prof_on ? clock64() : 0;
+        tma_store_wait_all<0>();
+        fire(k);
+        if (prof_on) w_done += clock64() - t0;
+      };
       auto take = [&]() -> uint8_t* {
-        mbar_wait_prof(&sfull[k & 1], (k >> 1) & 1, prof_on, w_sfull);
-        return staging + (k & 1) * kStagingBytes;
+        if (pend_n > 0 && !mbar_try_wait(&sfull[cur], kw[cur] & 1)) drain_all();   // idle: flush the signals
+        mbar_wait_prof(&sfull[cur], kw[cur] & 1, prof_on, w_sfull);
+        ++kw[cur];
+        return staging + cur * kStagingBytes;
       };
       auto issued = [&]() {
         tma_store_commit();
         ++k;
-        tma_store_wait_read<1>();              // everything but the newest group has been read out of smem
-        while (freed + 1 < k) { mbar_arrive(&sfree[freed & 1]); ++freed; }
+        tma_store_wait_read<0>();              // the chunk has been read out of smem: hand the buffer back at once
+        mbar_arrive(&sfree[cur]);
+        if (pend_n > 0 && k >= pend_seq[pend_head] + kSigLag) {
+          tma_store_wait_all<kSigLag>();       // groups 1..k-kSigLag are complete
+          fire(k - kSigLag);
+        }
       };
       uint32_t sitem = 0;
       while (sched.next(it)) {
+        cur = (int)(sitem & 1);
         trace_ev(p, 3, sitem, 0);
         if (it.type == 1) {
           const int row = it.g * p.M + it.t;
@@ -733,18 +848,22 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
         }
         trace_ev(p, 3, sitem, 1);
-        if (p.mode == 0 && it.type != 3) {
-          const long long t0 = prof_on ? clock64() : 0;
-          tma_store_wait_all<0>();             // the item's S / n_loc / S~ / den bytes are in global memory
-          if (prof_on) w_done += clock64() - t0;
-          while (freed < k) { mbar_arrive(&sfree[freed & 1]); ++freed; }
+        if (p.mode == 0 && it.type != 3 && p.sig_mode == 1) {
+          tma_store_wait_all<0>();
           fence_proxy_async_all();
           __threadfence();
           red_release_gpu_add(&p.counters[(it.type == 1 ? 0 : p.G) + it.g], 1u);
+        } else if (p.mode == 0 && it.type != 3) {
+          if (pend_n == kMaxPending) drain_all();
+          const int slot = (pend_head + pend_n) % kMaxPending;
+          pend_ptr[slot] = &p.counters[(it.type == 1 ? 0 : p.G) + it.g];
+          pend_seq[slot] = k;                  // the item's last group
+          ++pend_n;
         }
         trace_ev(p, 3, sitem, 2);
         ++sitem;
       }
+      drain_all();
       tma_store_wait_all<0>();
       if (prof_on) {
         unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;

@@ -18,6 +18,7 @@
 namespace mhla {
 
 constexpr int kChunk = 64;
+constexpr int kCausalThreads = 256;   // warps 0-3: producer / MMA / TMEM alloc / idle, 4-7: epilogue
 constexpr int kCTile = kChunk * 128;  // one [64 tokens][64 channels] 16-bit swizzle-128B tile = 8 KB
 constexpr int kPCol = 192;            // P accumulator columns [192,256) inside an accumulator buffer
 
@@ -72,7 +73,7 @@ struct CausalSched {
 };
 
 template <int DK, int DV>
-__global__ void __launch_bounds__(kThreads, 1) causal_kernel(const __grid_constant__ CausalParams p) {
+__global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_constant__ CausalParams p) {
   constexpr int DVH = DV > 128 ? 128 : DV;  // V columns per P3 item
   constexpr int NVH = DV / DVH;
   constexpr bool kKVOneStage = (DK + DV) <= 256;  // K and V tiles of one chunk fit one 32 KB stage
@@ -498,13 +499,13 @@ inline int causal_launch(CausalParams& P, const CausalPlan& pl, int unfused, int
     for (int mode = 1; mode <= 3; ++mode) {
       P.mode = mode;
       const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
-      kern<<<(int)(items < num_sms ? items : num_sms), kThreads, kSmemAlloc, stream>>>(P);
+      kern<<<(int)(items < num_sms ? items : num_sms), kCausalThreads, kSmemAlloc, stream>>>(P);
       ++*launches;
     }
   } else {
     P.mode = 0;
     const long long items = (long long)pl.G * (n1 + n2 + n3);
-    kern<<<(int)(items < num_sms ? items : num_sms), kThreads, kSmemAlloc, stream>>>(P);
+    kern<<<(int)(items < num_sms ? items : num_sms), kCausalThreads, kSmemAlloc, stream>>>(P);
     ++*launches;
   }
   return MHLA_OK;

@@ -292,6 +292,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   }
 
   P.prof = g_prof_buffer;
+  P.dep_mode = 0; P.sig_mode = 0;
+  if (const char* e = std::getenv("MHLA_DEPMODE")) P.dep_mode = std::atoi(e);
+  if (const char* e = std::getenv("MHLA_SIGMODE")) P.sig_mode = std::atoi(e);
   if (const char* e = std::getenv("MHLA_LAG2")) P.lag2 = std::atoi(e);   // tuning knobs (schedule distance, in groups,
   if (const char* e = std::getenv("MHLA_LAG3")) P.lag3 = std::atoi(e);   // between the phases of one (b,h) group)
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;

@@ -12,6 +12,10 @@ from mhla_b200 import _capi  # noqa: E402
 
 normalize = "--no-normalize" not in sys.argv
 tag = "norm" if normalize else "nonorm"
+kw = {}
+if "--p1only" in sys.argv:
+    kw = dict(unfused=True, debug_flags=_capi.FLAG_STOP_AFTER_P1)
+    tag += "_p1only"
 B, H, M, w, D = 2, 16, 128, 256, 64
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -23,11 +27,11 @@ out = torch.empty_like(q)
 L = _capi.lib()
 L.mhla_debug_set_profile_buffer.argtypes = [C.c_void_p]
 for _ in range(3):
-    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out)
+    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **kw)
 torch.cuda.synchronize()
 prof = torch.zeros(148 * 16 + 4 * 256 * 4, dtype=torch.int64, device=dev)
 L.mhla_debug_set_profile_buffer(prof.data_ptr())
-mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out)
+mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **kw)
 torch.cuda.synchronize()
 L.mhla_debug_set_profile_buffer(None)
 tr = prof[148 * 16:].cpu().view(4, 256, 4)
