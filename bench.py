@@ -138,7 +138,8 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--unfused", action="store_true", help="debug: run the three phases as separate launches")
+    ap.add_argument("--fused", action="store_true", help="single persistent kernel variant instead of the 3-launch default")
+    ap.add_argument("--unfused", action="store_true", help="(default path; kept for old command lines)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -168,7 +169,7 @@ def main():
     gathered = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=dev) if (args.gather and world > 1) else None
 
     def step():
-        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, unfused=args.unfused)
+        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=args.fused)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, out)
 
@@ -205,7 +206,7 @@ def main():
 
     def e2e_step():
         dq, dk, dv = hq.to(dev, non_blocking=True), hk.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
-        o = mhla_b200.mhla(dq, dk, dv, W, normalize=normalize)
+        o = mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, fused=args.fused)
         hout.copy_(o, non_blocking=True)
 
     e2e_step()

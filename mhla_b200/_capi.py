@@ -10,10 +10,12 @@ LIB_PATH = os.environ.get("MHLA_B200_LIB") or os.path.join(_HERE, "libmhla_b200.
 
 MHLA_BF16, MHLA_FP16 = 0, 1
 FLAG_NORMALIZE = 1 << 0
+FLAG_FUSED = 1 << 7
 FLAG_UNFUSED = 1 << 8
 FLAG_STOP_AFTER_P1 = 1 << 9
 FLAG_STOP_AFTER_P2 = 1 << 10
 FLAG_ONLY_P3 = 1 << 11
+FLAG_ONLY_P2 = 1 << 12
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",

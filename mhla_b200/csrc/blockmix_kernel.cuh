@@ -21,8 +21,10 @@
 namespace mhla {
 
 constexpr int kStageBytes = 32768;
-constexpr int kNumStages = 6;
-constexpr int kStagingBytes = 16384;  // x2 (double buffered epilogue staging, [128 rows][128 B] swizzle-128B)
+constexpr int kNumStages = 5;            // default ring depth (fused kernel, P2/P3 launches, causal kernel)
+constexpr int kMaxStages = 6;            // P1-only launches with D = 64 trade staging for a sixth stage
+constexpr int kStagingBytes = 16384;  // one staging slot: [128 rows][128 B] swizzle-128B tile
+constexpr int kStagingPerWg = 2 * kStagingBytes;   // each epilogue warpgroup owns two slots = one hand-off of <= 2 chunks
 constexpr int kThreads = 384;         // warp 0: TMA producer, 1: MMA issuer, 2: dependency poller (+TMEM alloc),
                                       // 3: store/signal, 4-7: epilogue warpgroup 0 (even items), 8-11: warpgroup 1 (odd items)
 constexpr int kEpiThreads = 128;
@@ -32,7 +34,7 @@ constexpr int kKsumCol = 128;         // ksum accumulator columns [128,144) insi
 
 constexpr int kSmemRing = 0;
 constexpr int kSmemStaging = kStageBytes * kNumStages;
-constexpr int kSmemOnes = kSmemStaging + 2 * kStagingBytes;
+constexpr int kSmemOnes = kSmemStaging + 2 * kStagingPerWg;
 constexpr int kSmemKsum = kSmemOnes + 512;
 constexpr int kSmemBars = kSmemKsum + 1024;   // ksum: 128 floats per epilogue warpgroup
 constexpr int kSmemTotal = kSmemBars + 256;
@@ -59,6 +61,7 @@ struct alignas(64) BlockmixParams {
   int lag2, lag3;
   float eps;
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
+  int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
   int dep_mode;                             // tuning: 0 = 32-lane dependency warp, 1 = single polling lane
   int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
 };
@@ -119,9 +122,12 @@ struct Sched {
 struct Ring {
   int stage = 0;
   uint32_t phase = 0;
+  int depth = kNumStages;
+  __device__ Ring() {}
+  __device__ explicit Ring(int d) : depth(d) {}
   __device__ __forceinline__ void advance(int n = 1) {
     stage += n;
-    while (stage >= kNumStages) { stage -= kNumStages; phase ^= 1; }
+    while (stage >= depth) { stage -= depth; phase ^= 1; }
   }
   __device__ __forceinline__ Ring at(int k) const { Ring r = *this; r.advance(k); return r; }
 };
@@ -151,12 +157,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem + kSmemRing;
-  uint8_t* staging = smem + kSmemStaging;
+  // smem carve-up: [ring: nst x 32 KB][staging: 2 warpgroups x 2 slots][ones][ksum][barriers]; ring + staging = 224 KB
+  const int nst = p.ring_stages;
+  const int slot_bytes = p.slot_bytes;          // one staging slot (16 KB; 8 KB in P1-only launches with D = 64)
+  uint8_t* staging = smem + nst * kStageBytes;
   uint16_t* ones = reinterpret_cast<uint16_t*>(smem + kSmemOnes);
   float* ksum_s = reinterpret_cast<float*>(smem + kSmemKsum);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
-  uint64_t* empty = full + kNumStages;
-  uint64_t* tfull = empty + kNumStages;
+  uint64_t* empty = full + kMaxStages;
+  uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
   uint64_t* sfull = tempty + 2;    // staging buffer written by the epilogue warps   (epilogue -> store warp)
   uint64_t* sfree = sfull + 2;     // staging buffer read out by TMA                 (store warp -> epilogue)
@@ -169,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   const uint32_t fmt16 = p.is_fp16 ? 0u : 1u;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kNumStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], 4); mbar_init(&sfree[i], 1);
     }
@@ -185,7 +194,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  grid_dependency_wait();   // PDL: everything above overlapped the tail of the prologue kernel (mix split, counters)
+  grid_dependency_wait();   // PDL: everything above overlapped the tail of the previous kernel in the stream
+  grid_launch_dependents(); // ... and the next kernel may start its own prologue as soon as SMs free up
 
   Sched sched; sched.init(p);
   Item it;
@@ -193,11 +203,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (warp == 0) {
     // ============================================================ TMA producer (one lane)
     if (lane == 0) {
-      Ring r;
+      Ring r(nst);
       uint32_t ndep = 0;   // dependency-bearing items seen so far
       const bool prof_on = p.prof != nullptr;
       long long w_empty = 0, w_dep = 0;
       const long long t_begin = clock64();
+      unsigned long long gt_begin;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_begin));
       uint32_t pitem = 0;
       auto wait_dependency = [&]() {
         // the dependency warp has already polled the group counter (global, ~1 us) - here it is a smem read
@@ -321,12 +333,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
         pr[0] = (unsigned long long)w_empty; pr[1] = (unsigned long long)w_dep;
         pr[2] = (unsigned long long)(clock64() - t_begin);
+        unsigned long long gt_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+        pr[14] = gt_end - gt_begin;   // nanoseconds: pr[2] / pr[14] = SM clock in GHz
       }
     }
   } else if (warp == 1) {
     // ============================================================ tcgen05 issuer (one lane)
     if (lane == 0) {
-      Ring r;
+      Ring r(nst);
       uint32_t nitem = 0;
       const bool prof_on = p.prof != nullptr;
       long long w_full = 0, w_tempty = 0;
@@ -525,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     ksum_s += wg * 128;
     const uint32_t bar_base = 1 + wg * 4;    // named barrier ids of this warpgroup
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    Ring r;
+    Ring r(nst);
     uint32_t nitem = 0;
     uint32_t nstore = 0;                     // staging buffer toggles per TMA-store chunk
     uint32_t v[32];
@@ -540,16 +555,22 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       for (int c = 0; c < 8; ++c)
         dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
     };
-    // staging hand-off with the store warp: warpgroup `wg` owns staging buffer `wg`; nstore counts its chunks
+    // Staging hand-off with the store warp.  Warpgroup `wg` owns two 16 KB slots; the chunks of an item are written
+    // alternately into them and handed over two at a time (one mbarrier round trip per pair - the round trip, not
+    // the copy, is what costs ~1500 cycles).  cj = chunk index within the item, nch = chunks of the item.
+    int cj = 0, nch = 0;
     auto staging_acquire = [&]() -> uint8_t* {
-      mbar_wait_prof(&sfree[wg], (nstore & 1) ^ 1, prof_on, w_sfree);   // first use passes immediately
-      return staging + wg * kStagingBytes;
+      if ((cj & 1) == 0) mbar_wait_prof(&sfree[wg], (nstore & 1) ^ 1, prof_on, w_sfree);   // first use passes immediately
+      return staging + wg * 2 * slot_bytes + (cj & 1) * slot_bytes;
     };
     auto staging_publish = [&]() {
       fence_proxy_async_smem();                 // my rows -> visible to the async proxy (TMA)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sfull[wg]);   // one arrival per epilogue warp
-      ++nstore;
+      ++cj;
+      if ((cj & 1) == 0 || cj == nch) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sfull[wg]);   // one arrival per epilogue warp
+        ++nstore;
+      }
     };
     // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
     auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
@@ -611,6 +632,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
       const long long t_item = prof_on ? clock64() : 0;
       if (et == 0) trace_ev(p, 2, nitem, 0);
+      cj = 0;
+      if (it.type == 1) nch = (p.normalize ? 1 : 0) + D / 64;
+      else if (it.type == 3) nch = p.nsub * (D / 64);
+      else {
+        const int tcx = it.t % p.n2_cols;
+        nch = 4;
+        if (tcx >= p.n2_scols) { const int rem = (2 * p.wpad - (tcx - p.n2_scols) * 256 + 31) / 32; nch = rem < 8 ? rem : 8; }
+      }
       if (it.type == 1) {
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) trace_ev(p, 2, nitem, 1);
@@ -784,23 +813,41 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       };
       uint32_t kw[2] = {0, 0};   // chunks taken from each warpgroup's staging buffer
       int cur = 0;               // warpgroup (= item parity) of the item being stored
+      int unfreed = -1;          // warpgroup whose previous hand-off has been issued but not yet handed back
       auto drain_all = [&]() {
         const long long t0 = prof_on ? clock64() : 0;
         tma_store_wait_all<0>();
+        if (unfreed >= 0) { mbar_arrive(&sfree[unfreed]); unfreed = -1; }
         fire(k);
         if (prof_on) w_done += clock64() - t0;
       };
+      int cj = 0, nch = 0;       // chunk index within the item / chunks of the item (same rule as the epilogue)
       auto take = [&]() -> uint8_t* {
-        if (pend_n > 0 && !mbar_try_wait(&sfull[cur], kw[cur] & 1)) drain_all();   // idle: flush the signals
-        mbar_wait_prof(&sfull[cur], kw[cur] & 1, prof_on, w_sfull);
-        ++kw[cur];
-        return staging + cur * kStagingBytes;
+        if ((cj & 1) == 0) {
+          if (pend_n > 0 && !mbar_try_wait(&sfull[cur], kw[cur] & 1)) drain_all();   // idle: flush the signals
+          mbar_wait_prof(&sfull[cur], kw[cur] & 1, prof_on, w_sfull);
+          ++kw[cur];
+        }
+        return staging + cur * 2 * slot_bytes + (cj & 1) * slot_bytes;
       };
+      // Buffers are handed back lazily: the TMA store engine drains a 32 KB pair in ~2000 cycles, so blocking on every
+      // read-out would make this lane the bottleneck.  After committing hand-off k we only wait until hand-off k-1 has
+      // been read (`wait_group.read 1`) - unless the same warpgroup produces the next hand-off too (an item with more
+      // than two chunks), in which case its slots must come back before it can continue.
       auto issued = [&]() {
+        ++cj;
+        if ((cj & 1) != 0 && cj != nch) return;   // second chunk of the pair still to come
         tma_store_commit();
         ++k;
-        tma_store_wait_read<0>();              // the chunk has been read out of smem: hand the buffer back at once
-        mbar_arrive(&sfree[cur]);
+        if (cj != nch) {                       // more hand-offs of this item follow from the same warpgroup
+          tma_store_wait_read<0>();
+          if (unfreed >= 0) { mbar_arrive(&sfree[unfreed]); unfreed = -1; }
+          mbar_arrive(&sfree[cur]);
+        } else {
+          tma_store_wait_read<1>();            // everything but the newest group has been read out of smem
+          if (unfreed >= 0) mbar_arrive(&sfree[unfreed]);
+          unfreed = cur;
+        }
         if (pend_n > 0 && k >= pend_seq[pend_head] + kSigLag) {
           tma_store_wait_all<kSigLag>();       // groups 1..k-kSigLag are complete
           fire(k - kSigLag);
@@ -809,6 +856,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       uint32_t sitem = 0;
       while (sched.next(it)) {
         cur = (int)(sitem & 1);
+        cj = 0;
+        if (it.type == 1) nch = (p.normalize ? 1 : 0) + D / 64;
+        else if (it.type == 3) nch = p.nsub * (D / 64);
+        else {
+          const int tcx = it.t % p.n2_cols;
+          nch = 4;
+          if (tcx >= p.n2_scols) { const int rem = (2 * p.wpad - (tcx - p.n2_scols) * 256 + 31) / 32; nch = rem < 8 ? rem : 8; }
+        }
         trace_ev(p, 3, sitem, 0);
         if (it.type == 1) {
           const int row = it.g * p.M + it.t;

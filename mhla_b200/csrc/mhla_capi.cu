@@ -313,31 +313,42 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
                                                d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
   ++launches;
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
-  if (d->flags & MHLA_FLAG_UNFUSED) {
-    const int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
-    const int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
-    for (int mode = first; mode <= last; ++mode) {
-      P.mode = mode;
-      const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
-      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-      kern<<<grid, mhla::kThreads, mhla::kSmemAlloc, stream>>>(P);
-      ++launches;
-    }
-  } else {
-    P.mode = 0;
-    const long long items = (long long)pl.G * (n1 + n2 + n3);
-    const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+  auto launch_pdl = [&](int grid) -> bool {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(mhla::kThreads);
     cfg.dynamicSmemBytes = mhla::kSmemAlloc;
     cfg.stream = stream;
     cudaLaunchAttribute attrs[1];
-    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap our prologue with the mix-split kernel
+    attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // prologue overlaps the previous kernel's tail
     attrs[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
     cfg.numAttrs = 1;
-    if (!cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx")) return MHLA_ERR_CUDA;
+    return cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx");
+  };
+  if (!(d->flags & MHLA_FLAG_FUSED)) {
+    int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
+    int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
+    if (d->flags & MHLA_FLAG_ONLY_P2) first = last = 2;
+    for (int mode = first; mode <= last; ++mode) {
+      P.mode = mode;
+      // P1 with D = 64 only stages 1 KB (n_loc) + 8 KB (S) per item: give the ring a sixth stage instead (a multiple
+      // of the 3 stages per item keeps the long-lived Q stage out of the K/V recycling path)
+      const bool small_staging = (mode == 1 && d->D == 64);
+      P.slot_bytes = small_staging ? 8192 : 16384;
+      P.ring_stages = small_staging ? 6 : 5;
+      const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
+      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+      if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
+      ++launches;
+    }
+  } else {
+    P.mode = 0;
+    P.slot_bytes = 16384;
+    P.ring_stages = 5;
+    const long long items = (long long)pl.G * (n1 + n2 + n3);
+    const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+    if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
     ++launches;
   }
   if (!cuda_ok(cudaGetLastError(), "kernel launch")) return MHLA_ERR_CUDA;

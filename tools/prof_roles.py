@@ -22,13 +22,13 @@ out = torch.empty_like(q)
 L = _capi.lib()
 L.mhla_debug_set_profile_buffer.argtypes = [C.c_void_p]
 for _ in range(3):
-    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out)
+    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=True)
 torch.cuda.synchronize()
 prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
 L.mhla_debug_set_profile_buffer(prof.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out)
+mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=True)
 e1.record()
 torch.cuda.synchronize()
 L.mhla_debug_set_profile_buffer(None)
@@ -37,6 +37,7 @@ names = ["prod.wait_empty", "prod.wait_dep", "prod.total", "mma.wait_full", "mma
          "epi.wait_sfree", "epi.wait_qfull", "epi.t_P1", "epi.t_P2", "epi.t_P3", "epi.items", "store.wait_sfull",
          "store.wait_done"]
 print(f"normalize={normalize}  step (events) = {e0.elapsed_time(e1) * 1e3:.1f} us")
+print("SM clock (GHz) from clock64/globaltimer over the producer lifetime: mean %.3f min %.3f max %.3f ; lifetime us mean %.1f" % ((p[:,2]/p[:,14]).mean(), (p[:,2]/p[:,14]).min(), (p[:,2]/p[:,14]).max(), p[:,14].mean()/1e3))
 tot = p[:, 2].mean()
 for i, n in enumerate(names):
     col = p[:, i]
