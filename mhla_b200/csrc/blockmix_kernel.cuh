@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 
   if (warp == 0) {
     // ============================================================ TMA producer (one lane)
-    if (lane == 0) {
+    if (elect_one()) {
       Ring r(nst);
       uint32_t ndep = 0;   // dependency-bearing items seen so far
       const bool prof_on = p.prof != nullptr;
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ============================================================ tcgen05 issuer (one lane)
-    if (lane == 0) {
+    if (elect_one()) {
       Ring r(nst);
       uint32_t nitem = 0;
       const bool prof_on = p.prof != nullptr;
@@ -790,7 +790,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // Issues every TMA store (so the bulk async-groups belong to this thread), recycles the staging buffers and
     // publishes the per-group dependency counters once an item's stores have fully completed - none of this sits on
     // the epilogue warps' critical path.
-    if (lane == 0) {
+    if (elect_one()) {
       uint32_t k = 0;              // bulk groups committed so far
       const bool prof_on = p.prof != nullptr;
       long long w_sfull = 0, w_done = 0;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
 
   if (warp == 0) {
     // ============================================================ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
       Ring r;
       while (sched.next(it)) {
         const int b = it.g / p.H, h = it.g % p.H;
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
     }
   } else if (warp == 1) {
     // ============================================================ tcgen05 issuer
-    if (lane == 0) {
+    if (elect_one()) {
       Ring r;
       uint32_t nitem = 0;
       uint32_t pcnt[2] = {0, 0};   // P3 items seen per accumulator buffer (phase of pfull / pready)
