@@ -11,11 +11,15 @@
 //                    formulation is not possible: tcgen05 kind::tf32 returns zeros for an MN-major operand with
 //                    the plain 128B swizzle - see profiles/r01_microtest_umma_layouts.log)
 //   P3 (g, i)        O_i = (Q_i S~_i) / den_i
-// Items of different (b,h) groups g are interleaved in a fixed global order (P1(s), P3(s-lag3), P2(s-lag2))
-// so that the S / S~ / den workspace and the second read of Q are served from L2; cross-CTA dependencies
-// are per-group arrival counters in global memory (release/acquire), all CTAs are co-resident.
+// Every item has a fixed owner CTA (linear item index mod grid size), but the ORDER in which a CTA runs its P1 / P2 /
+// P3 items is decided at run time by a scheduler warp: a dependent item (P2 needs all P1 of its group, P3 all P2) is
+// only enqueued once its group's arrival counter in global memory (release/acquire) says it is ready, ready P2 and
+// P3 items go before new P1 items, and P1 may run at most `window` groups ahead of the CTA's next P3 item - so the
+// S / S~ / den workspace and the second read of Q are served from L2 and no role ever blocks on a dependency.
+// The scheduler feeds the other roles through a small FIFO in shared memory; all CTAs are co-resident.
 #pragma once
 #include <cuda.h>
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace mhla {
@@ -37,7 +41,9 @@ constexpr int kSmemStaging = kStageBytes * kNumStages;
 constexpr int kSmemOnes = kSmemStaging + 2 * kStagingPerWg;
 constexpr int kSmemKsum = kSmemOnes + 512;
 constexpr int kSmemBars = kSmemKsum + 1024;   // ksum: 128 floats per epilogue warpgroup
-constexpr int kSmemTotal = kSmemBars + 256;
+constexpr int kSmemFifo = kSmemBars + 256;    // scheduler -> roles item FIFO
+constexpr int kFifoDepth = 64;
+constexpr int kSmemTotal = kSmemFifo + kFifoDepth * 4;
 constexpr int kSmemAlloc = kSmemTotal + 1024;  // slack for manual 1024-byte alignment
 
 struct alignas(64) BlockmixParams {
@@ -50,6 +56,7 @@ struct alignas(64) BlockmixParams {
   CUtensorMap tmStld;                       // S~ load   : (Dv, Dk, G*M)      bf16/fp16, box (64, Dk, 1)
   CUtensorMap tmO;                          // out       : rank-5 like q
   uint16_t* ws_S;                           // [G*M][ncols] 16-bit: S_j (Dk*Dv) | n_loc_j hi (wpad) | n_loc_j lo (wpad)
+  uint16_t* ws_St;                          // [G*M][Dk*Dv] 16-bit: S~_i
   const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
   int G, H, M, w, TW, nsub;
@@ -58,17 +65,23 @@ struct alignas(64) BlockmixParams {
   int kslabs;                               // ceil(M / 64)
   int normalize, ropenorm, is_fp16;
   int mode;                                 // 0: fused; 1/2/3: only that phase (unfused debugging path)
-  int lag2, lag3;
+  int window;                               // fused mode: P1 may run this many groups ahead of the CTA's next P3 item
+  int run_ahead;                            // fused mode: items the scheduler may enqueue ahead of the producer
+  int np2;                                  // fused mode: CTAs [0, np2) run only P2 items (0: every CTA owns P2 items too)
   float eps;
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
-  int dep_mode;                             // tuning: 0 = 32-lane dependency warp, 1 = single polling lane
   int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
+  int policy;                               // mode 0: 0 = ready P3 items before new P1 items (window), 1 = P3 items last
+  int reverse3;                             // mode 3: walk the groups backwards
+  int pf_dist;                              // L2 prefetch distance of the producer, in own streaming items (0: off)
+  int trace_cta;                            // debug: CTA whose event trace is recorded
+  int cnt_stride;                           // words between two dependency counters (padded to separate L2 sectors)
 };
 
 // Event trace of CTA 0 (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
 __device__ __forceinline__ void trace_ev(const BlockmixParams& p, int role, uint32_t item, int slot) {
-  if (p.prof != nullptr && blockIdx.x == 0 && item < 256)
+  if (p.prof != nullptr && (int)blockIdx.x == p.trace_cta && item < 256)
     p.prof[(size_t)gridDim.x * 16 + ((size_t)role * 256 + item) * 4 + slot] = (unsigned long long)clock64();
 }
 
@@ -84,38 +97,44 @@ struct Item {
   int type, g, t;
 };
 
-struct Sched {
-  int G, n1, n2, n3, lag2, lag3, mode, nsteps, stride;
-  int s;
-  long long off;
-  __device__ void init(const BlockmixParams& p) {
-    G = p.G; n1 = p.M; n2 = p.n2_rows * p.n2_cols; n3 = p.M;
-    lag2 = p.lag2; lag3 = p.lag3; mode = p.mode;
-    nsteps = G + (lag2 > lag3 ? lag2 : lag3);
-    stride = gridDim.x; s = 0; off = blockIdx.x;
+// Item FIFO entry: type [0,2) | g [2,16) | t [16,32); type 0 terminates the stream.
+__device__ __forceinline__ uint32_t fifo_encode(int type, int g, int t) {
+  return (uint32_t)type | ((uint32_t)g << 2) | ((uint32_t)t << 16);
+}
+
+// Consumer side of the item FIFO (one per role; every role sees the same item sequence).
+struct ItemStream {
+  const uint32_t* fifo;
+  const uint32_t* published;
+  uint32_t idx = 0;
+  __device__ ItemStream(const uint32_t* f, const uint32_t* pub) : fifo(f), published(pub) {}
+  __device__ __forceinline__ bool ready() const { return ld_acquire_cta_shared(published) > idx; }
+  // single-lane roles
+  __device__ __forceinline__ bool next(Item& it) {
+    uint32_t spins = 0;
+    while (!ready()) {
+      __nanosleep(20);   // keep the poll off the shared-memory pipe the epilogue warps of this SM sub-partition use
+      if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: item stream stalled (block %d)\n", blockIdx.x); __trap(); }
+    }
+    return take(it);
   }
-  __device__ bool next(Item& it) {
-    if (mode != 0) {
-      const int n = mode == 1 ? n1 : (mode == 2 ? n2 : n3);
-      if (off >= (long long)G * n) return false;
-      it.type = mode; it.g = (int)(off / n); it.t = (int)(off % n);
-      off += stride;
-      return true;
+  // whole-warp roles: one lane polls, the warp then reads the entry together
+  __device__ __forceinline__ bool next_warp(Item& it, int lane) {
+    if (lane == 0) {
+      uint32_t spins = 0;
+      while (!ready()) {
+        __nanosleep(32);
+        if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: item stream stalled (block %d)\n", blockIdx.x); __trap(); }
+      }
     }
-    while (s < nsteps) {
-      const int c1 = (s < G) ? n1 : 0;
-      const int g3 = s - lag3, g2 = s - lag2;
-      const int c3 = (g3 >= 0 && g3 < G) ? n3 : 0;
-      const int c2 = (g2 >= 0 && g2 < G) ? n2 : 0;
-      const int tot = c1 + c3 + c2;
-      if (off >= tot) { off -= tot; ++s; continue; }
-      if (off < c1) { it.type = 1; it.g = s; it.t = (int)off; }
-      else if (off < c1 + c3) { it.type = 3; it.g = g3; it.t = (int)off - c1; }
-      else { it.type = 2; it.g = g2; it.t = (int)off - c1 - c3; }
-      off += stride;
-      return true;
-    }
-    return false;
+    __syncwarp();
+    return take(it);
+  }
+  __device__ __forceinline__ bool take(Item& it) {
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t*>(fifo + (idx & (kFifoDepth - 1)));
+    ++idx;
+    it.type = (int)(e & 3u); it.g = (int)((e >> 2) & 0x3FFFu); it.t = (int)(e >> 16);
+    return it.type != 0;
   }
 };
 
@@ -123,8 +142,10 @@ struct Ring {
   int stage = 0;
   uint32_t phase = 0;
   int depth = kNumStages;
+  int base = 0;     // first physical stage of this ring (stages below it hold resident data)
   __device__ Ring() {}
-  __device__ explicit Ring(int d) : depth(d) {}
+  __device__ explicit Ring(int d, int b = 0) : depth(d - b), base(b) {}
+  __device__ __forceinline__ int idx() const { return base + stage; }
   __device__ __forceinline__ void advance(int n = 1) {
     stage += n;
     while (stage >= depth) { stage -= depth; phase ^= 1; }
@@ -170,12 +191,21 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint64_t* sfull = tempty + 2;    // staging buffer written by the epilogue warps   (epilogue -> store warp)
   uint64_t* sfree = sfull + 2;     // staging buffer read out by TMA                 (store warp -> epilogue)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
-  uint32_t* dep_count = tmem_slot + 1;   // dependencies confirmed by the dependency warp (warp 2), read by the producer
+  uint32_t* q_published = tmem_slot + 1;   // items the scheduler warp (warp 2) has enqueued
+  uint32_t* q_started = tmem_slot + 2;     // items the producer has picked up (throttles the scheduler's run-ahead)
+  uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished by each epilogue warpgroup
+  uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + kSmemFifo);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tile_bytes = p.TW * 128;  // one [TW rows][64 x 16-bit] swizzle-128B tile
   const uint32_t fmt16 = p.is_fp16 ? 0u : 1u;
+  // Dedicated block-mixing CTA of the fused kernel: the mixing matrix (hi | lo, one ring stage per 64-block slab) stays
+  // resident in ring stages [0, kslabs) and only the S / n_loc tiles stream through the remaining stages.
+  // in-kernel dependencies through the per-group counters: 0 = all phases, 4 = P1 + P2 only, 5 = P3 only, started by PDL
+  // while the mode-4 grid is still draining (no griddepcontrol.wait: the counters carry the dependency)
+  const bool dynamic = p.mode == 0 || p.mode == 4 || p.mode == 5;
+  const bool wres = dynamic && (int)blockIdx.x < p.np2 && p.n2_rows == 1 && p.kslabs <= 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -183,7 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], 4); mbar_init(&sfree[i], 1);
     }
     fence_barrier_init();
-    *dep_count = 0;
+    *q_published = 0;
+    *q_started = 0;
+    wg_done[0] = 0; wg_done[1] = 0;
     const CUtensorMap* maps = &p.tmK;
     for (int i = 0; i < 12; ++i) tma_prefetch_desc(maps + i);
   }
@@ -194,137 +226,174 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  grid_dependency_wait();   // PDL: everything above overlapped the tail of the previous kernel in the stream
+  if (p.mode != 5) grid_dependency_wait();   // PDL: everything above overlapped the tail of the previous kernel in the stream
   grid_launch_dependents(); // ... and the next kernel may start its own prologue as soon as SMs free up
+  // debug timeline: [mode][cta] = {globaltimer at start of work, at end}, behind the per-CTA counters and the CTA trace
+  unsigned long long* const tl = p.prof == nullptr ? nullptr
+      : p.prof + (size_t)gridDim.x * 16 + 4 * 256 * 4 + ((size_t)p.mode * 148 + blockIdx.x) * 2;
+  if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[0] = t; }
 
-  Sched sched; sched.init(p);
+  ItemStream sched(fifo, q_published);
   Item it;
 
   if (warp == 0) {
     // ============================================================ TMA producer (one lane)
     if (elect_one()) {
-      Ring r(nst);
-      uint32_t ndep = 0;   // dependency-bearing items seen so far
+      Ring r(nst, wres ? p.kslabs : 0);
       const bool prof_on = p.prof != nullptr;
       long long w_empty = 0, w_dep = 0;
       const long long t_begin = clock64();
       unsigned long long gt_begin;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_begin));
       uint32_t pitem = 0;
-      auto wait_dependency = [&]() {
-        // the dependency warp has already polled the group counter (global, ~1 us) - here it is a smem read
-        uint32_t spins = 0;
-        const long long t0 = clock64();
-        while (ld_acquire_cta_shared(dep_count) <= ndep) {
-          if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
-        }
-        ++ndep;
-        fence_proxy_async_all();
-        w_dep += clock64() - t0;
-        trace_ev(p, 0, pitem, 2);
+      // A dependent item is only enqueued after the scheduler lane has acquired its group's counter; the FIFO hand-off
+      // (release/acquire in shared memory) extends that to this lane, the proxy fence to the TMA loads issued below.
+      auto wait_dependency = [&]() { fence_proxy_async_all(); };
+      // The streaming items a CTA owns are a fixed arithmetic sequence of linear block indices, so the producer can pull
+      // the tiles of the item `pf_dist` places further down its own list into L2 while it fills shared memory for the
+      // current one: the shared-memory fill then sees L2 latency instead of HBM latency, and the bytes in flight towards
+      // HBM are no longer bounded by the ring.
+      const long long n1tot_p = (long long)p.G * p.M;
+      const long long nct13_p = (dynamic && p.np2 > 0) ? (long long)gridDim.x - p.np2 : (long long)gridDim.x;
+      auto prefetch_block = [&](long long idx, bool kv, bool q_norm, bool q_read) {
+        if (p.pf_dist <= 0) return;
+        idx += (long long)p.pf_dist * nct13_p;
+        if (idx >= n1tot_p) return;
+        const int g_ = (int)(idx / p.M), j_ = (int)(idx % p.M);
+        const int b_ = g_ / p.H, h_ = g_ % p.H;
+        for (int sub = 0; sub < p.nsub; ++sub)
+          for (int c0 = 0; c0 < D; c0 += 64) {
+            if (kv) {
+              tma_prefetch_5d(&p.tmK, c0, sub * p.TW, j_, h_, b_);
+              tma_prefetch_5d(&p.tmV, c0, sub * p.TW, j_, h_, b_);
+              if (p.ropenorm) tma_prefetch_5d(&p.tmKn, c0, sub * p.TW, j_, h_, b_);
+            }
+            if (q_norm) tma_prefetch_5d(&p.tmQn, c0, sub * p.TW, j_, h_, b_);
+            if (q_read) tma_prefetch_5d(&p.tmQr, c0, sub * p.TW, j_, h_, b_);
+          }
       };
-      while (sched.next(it)) {
+      if (wres) {
+        for (int slab = 0; slab < p.kslabs; ++slab) {
+          uint8_t* st = ring + slab * kStageBytes;
+          mbar_arrive_expect_tx(&full[slab], 32768);
+          tma_load_3d(st, &p.tmW, &full[slab], slab * 64, 0, 0, kEvictLast);
+          tma_load_3d(st + 16384, &p.tmW, &full[slab], slab * 64, 0, 1, kEvictLast);
+        }
+      }
+      while (true) {
+        const long long tq0 = prof_on ? clock64() : 0;
+        const bool more = sched.next(it);
+        if (prof_on) w_dep += clock64() - tq0;      // time spent waiting for the scheduler (nothing ready)
+        if (!more) break;
+        st_release_cta_shared(q_started, sched.idx);
         const int b = it.g / p.H, h = it.g % p.H;
         trace_ev(p, 0, pitem, 0);
-        if (p.prof != nullptr && blockIdx.x == 0 && pitem < 256)
+        if (p.prof != nullptr && (int)blockIdx.x == p.trace_cta && pitem < 256)
           p.prof[(size_t)gridDim.x * 16 + ((size_t)0 * 256 + pitem) * 4 + 3] = (unsigned long long)it.type;
         if (it.type == 1) {
           const int j = it.t;
           for (int sub = 0; sub < p.nsub; ++sub) {
             const int t0 = sub * p.TW;
             if constexpr (D == 64) {
-              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-              uint8_t* st = ring + r.stage * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
-              tma_load_5d(st, &p.tmK, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
-              tma_load_5d(st + 16384, &p.tmV, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              uint8_t* st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
+              tma_load_5d(st, &p.tmK, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
+              tma_load_5d(st + 16384, &p.tmV, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
               r.advance();
             } else {
               for (int kv = 0; kv < 2; ++kv) {
-                mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-                uint8_t* st = ring + r.stage * kStageBytes;
-                mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
+                mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+                uint8_t* st = ring + r.idx() * kStageBytes;
+                mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
                 const CUtensorMap* tm = kv ? &p.tmV : &p.tmK;
-                tma_load_5d(st, tm, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
-                tma_load_5d(st + 16384, tm, &full[r.stage], 64, t0, j, h, b, kEvictFirst);
+                tma_load_5d(st, tm, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
+                tma_load_5d(st + 16384, tm, &full[r.idx()], 64, t0, j, h, b, kEvictFirst);
                 r.advance();
               }
             }
             if (p.ropenorm) {
-              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-              uint8_t* st = ring + r.stage * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.stage], (D / 64) * tile_bytes);
-              tma_load_5d(st, &p.tmKn, &full[r.stage], 0, t0, j, h, b, kEvictFirst);
-              if constexpr (D == 128) tma_load_5d(st + 16384, &p.tmKn, &full[r.stage], 64, t0, j, h, b, kEvictFirst);
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              uint8_t* st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], (D / 64) * tile_bytes);
+              tma_load_5d(st, &p.tmKn, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
+              if constexpr (D == 128) tma_load_5d(st + 16384, &p.tmKn, &full[r.idx()], 64, t0, j, h, b, kEvictFirst);
               r.advance();
             }
           }
           if (p.normalize) {
             if constexpr (D == 64) {
-              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-              uint8_t* st = ring + r.stage * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.stage], p.nsub * tile_bytes);
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              uint8_t* st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], p.nsub * tile_bytes);
               for (int sub = 0; sub < p.nsub; ++sub)
-                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.stage], 0, sub * p.TW, j, h, b, kEvictLast);
+                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, kEvictLast);
               r.advance();
             } else {
               for (int sub = 0; sub < p.nsub; ++sub) {
-                mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-                uint8_t* st = ring + r.stage * kStageBytes;
-                mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
-                tma_load_5d(st, &p.tmQn, &full[r.stage], 0, sub * p.TW, j, h, b, kEvictLast);
-                tma_load_5d(st + 16384, &p.tmQn, &full[r.stage], 64, sub * p.TW, j, h, b, kEvictLast);
+                mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+                uint8_t* st = ring + r.idx() * kStageBytes;
+                mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
+                tma_load_5d(st, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, kEvictLast);
+                tma_load_5d(st + 16384, &p.tmQn, &full[r.idx()], 64, sub * p.TW, j, h, b, kEvictLast);
                 r.advance();
               }
             }
           }
+          // (after this item's own loads: the TMA unit serves its queue in order)
+          prefetch_block((long long)it.g * p.M + j, true, p.normalize != 0, false);
         } else if (it.type == 2) {
-          if (p.mode == 0) wait_dependency();
+          if (dynamic) wait_dependency();
           const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
           for (int slab = 0; slab < p.kslabs; ++slab) {
             // stage X: mix hi | mix lo, [128 i][64 j] each; stage Y: [64 j][256 cols] as 4 tiles of 64 columns
-            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-            uint8_t* st = ring + r.stage * kStageBytes;
-            mbar_arrive_expect_tx(&full[r.stage], 32768);
-            tma_load_3d(st, &p.tmW, &full[r.stage], slab * 64, ti * 128, 0, kEvictLast);
-            tma_load_3d(st + 16384, &p.tmW, &full[r.stage], slab * 64, ti * 128, 1, kEvictLast);
-            r.advance();
-            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-            st = ring + r.stage * kStageBytes;
-            mbar_arrive_expect_tx(&full[r.stage], 32768);
+            uint8_t* st;
+            if (!wres) {
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], 32768);
+              tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
+              tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
+              r.advance();
+            }
+            mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+            st = ring + r.idx() * kStageBytes;
+            mbar_arrive_expect_tx(&full[r.idx()], 32768);
             for (int n4 = 0; n4 < 4; ++n4)
-              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.stage], tc * 256 + n4 * 64, slab * 64, it.g, kEvictNormal);
+              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.idx()], tc * 256 + n4 * 64, slab * 64, it.g, kEvictNormal);
             r.advance();
           }
         } else {
-          if (p.mode == 0) wait_dependency();
+          if (dynamic) wait_dependency();
           const int i = it.t;
           const CUtensorMap* tq = &p.tmQr;
           if constexpr (D == 64) {
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-              uint8_t* st = ring + r.stage * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.stage], tile_bytes + (sub == 0 ? 8192 : 0));
-              tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
-              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.stage], 0, 0, it.g * p.M + i, kEvictFirst);
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              uint8_t* st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], tile_bytes + (sub == 0 ? 8192 : 0));
+              tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
+              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, it.g * p.M + i, kEvictFirst);
               r.advance();
             }
           } else {
-            mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-            uint8_t* st = ring + r.stage * kStageBytes;
-            mbar_arrive_expect_tx(&full[r.stage], 32768);
-            tma_load_3d(st, &p.tmStld, &full[r.stage], 0, 0, it.g * p.M + i, kEvictFirst);
-            tma_load_3d(st + 16384, &p.tmStld, &full[r.stage], 64, 0, it.g * p.M + i, kEvictFirst);
+            mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+            uint8_t* st = ring + r.idx() * kStageBytes;
+            mbar_arrive_expect_tx(&full[r.idx()], 32768);
+            tma_load_3d(st, &p.tmStld, &full[r.idx()], 0, 0, it.g * p.M + i, kEvictFirst);
+            tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 64, 0, it.g * p.M + i, kEvictFirst);
             r.advance();
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait_prof(&empty[r.stage], r.phase ^ 1, prof_on, w_empty);
-              st = ring + r.stage * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.stage], 2 * tile_bytes);
-              tma_load_5d(st, tq, &full[r.stage], 0, sub * p.TW, i, h, b, kEvictFirst);
-              tma_load_5d(st + 16384, tq, &full[r.stage], 64, sub * p.TW, i, h, b, kEvictFirst);
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              st = ring + r.idx() * kStageBytes;
+              mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
+              tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
+              tma_load_5d(st + 16384, tq, &full[r.idx()], 64, sub * p.TW, i, h, b, kEvictFirst);
               r.advance();
             }
           }
+          // the readout's Q tile has not been read before unless the normaliser pulled the same tensor through L2
+          if (!p.normalize || p.ropenorm || p.mode != 0) prefetch_block((long long)it.g * p.M + i, false, false, true);
         }
         trace_ev(p, 0, pitem, 1);
         ++pitem;
@@ -341,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   } else if (warp == 1) {
     // ============================================================ tcgen05 issuer (one lane)
     if (elect_one()) {
-      Ring r(nst);
+      Ring r(nst, wres ? p.kslabs : 0);
       uint32_t nitem = 0;
       const bool prof_on = p.prof != nullptr;
       long long w_full = 0, w_tempty = 0;
@@ -373,16 +442,16 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint32_t a_addr, b_addr;
             Ring r0 = r;
             if constexpr (D == 64) {
-              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
-              a_addr = ring_addr + r.stage * kStageBytes;
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+              a_addr = ring_addr + r.idx() * kStageBytes;
               b_addr = a_addr + 16384;
               r.advance();
             } else {
-              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
-              a_addr = ring_addr + r.stage * kStageBytes;
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+              a_addr = ring_addr + r.idx() * kStageBytes;
               r.advance();
-              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
-              b_addr = ring_addr + r.stage * kStageBytes;
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+              b_addr = ring_addr + r.idx() * kStageBytes;
               r.advance();
             }
             tc_fence_after();
@@ -405,21 +474,21 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               for (int ks = 0; ks < 8; ++ks)
                 if (ks < ksteps) mma_f16_ss(acc, da0 + ks * 128, db0 + ks * 128, idesc_p1, ks ? 1u : first);
             }
-            mma_commit(&empty[r0.stage]);
-            if constexpr (D == 128) mma_commit(&empty[r0.at(1).stage]);
+            mma_commit(&empty[r0.idx()]);
+            if constexpr (D == 128) mma_commit(&empty[r0.at(1).idx()]);
             if (p.ropenorm) {
               // ksum of the un-roped K (variant B with the normaliser) from its own stage.  NOTE: issued as a plain
               // (not unrolled, descriptor rebuilt per step) loop on purpose - a full-speed back-to-back run of these
               // narrow N=16 accumulating MMAs gave wrong sums on B200 (profiles/r01_bringup_notes.md).
-              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
               tc_fence_after();
-              const uint32_t n_addr = ring_addr + r.stage * kStageBytes;
+              const uint32_t n_addr = ring_addr + r.idx() * kStageBytes;
 #pragma unroll 1
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t da = make_smem_desc(n_addr + ks * 2048, 16384, 1024, kSwizzle128);
                 mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
               }
-              mma_commit(&empty[r.stage]);
+              mma_commit(&empty[r.idx()]);
               r.advance();
             }
           }
@@ -427,22 +496,29 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (p.normalize) r.advance(D == 64 ? 1 : p.nsub);  // Q stages are consumed by the epilogue warps
         } else if (it.type == 2) {
           for (int slab = 0; slab < p.kslabs; ++slab) {
-            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
-            const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
-            const int sa = r.stage;
-            r.advance();
-            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
+            uint32_t a_addr;
+            int sa = -1;
+            if (wres) {
+              if (nitem == 0) mbar_wait_prof(&full[slab], 0, prof_on, w_full);   // resident mixing matrix: loaded once
+              a_addr = ring_addr + slab * kStageBytes;
+            } else {
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+              a_addr = ring_addr + r.idx() * kStageBytes;
+              sa = r.idx();
+              r.advance();
+            }
+            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
             tc_fence_after();
             const uint64_t dhi0 = dsc(tmpl_k, a_addr), dlo0 = dsc(tmpl_k, a_addr + 16384);   // K-major: 32 B per k-step
-            const uint64_t db0 = dsc(tmpl_mn8k, ring_addr + r.stage * kStageBytes);           // MN-major: 2048 B per k-step
+            const uint64_t db0 = dsc(tmpl_mn8k, ring_addr + r.idx() * kStageBytes);           // MN-major: 2048 B per k-step
             const uint32_t first = slab != 0;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
               mma_f16_ss(acc, dlo0 + ks * 2, db0 + ks * 128, idesc_p2, 1u);
             }
-            mma_commit(&empty[sa]);
-            mma_commit(&empty[r.stage]);
+            if (sa >= 0) mma_commit(&empty[sa]);
+            mma_commit(&empty[r.idx()]);
             r.advance();
           }
           mma_commit(&tfull[ab]);
@@ -450,14 +526,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           Ring r0 = r;
           uint32_t b_addr;
           if constexpr (D == 128) {
-            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
-            b_addr = ring_addr + r.stage * kStageBytes;
+            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+            b_addr = ring_addr + r.idx() * kStageBytes;
             r.advance();
           }
           for (int sub = 0; sub < p.nsub; ++sub) {
-            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_full);
+            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
             tc_fence_after();
-            const uint32_t a_addr = ring_addr + r.stage * kStageBytes;
+            const uint32_t a_addr = ring_addr + r.idx() * kStageBytes;
             if constexpr (D == 64) { if (sub == 0) b_addr = a_addr + 16384; }
             const uint64_t da0 = dsc(tmpl_k, a_addr), db0 = dsc(tmpl_mn16k, b_addr);
 #pragma unroll
@@ -466,7 +542,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             r.advance();
           }
           const int ns = p3_stages<D>(p);
-          for (int k = 0; k < ns; ++k) mma_commit(&empty[r0.at(k).stage]);
+          for (int k = 0; k < ns; ++k) mma_commit(&empty[r0.at(k).idx()]);
           mma_commit(&tfull[ab]);
         }
         trace_ev(p, 1, nitem, 2);
@@ -478,106 +554,187 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
     }
   } else if (warp == 2) {
-    // ============================================================ dependency warp (32 lanes)
-    // Polls the per-group counters in global memory for the producer.  An L2 round trip under load costs microseconds,
-    // so the 32 lanes watch the next 32 dependency-bearing items concurrently (lane L owns dependencies L, L+32, ...)
-    // and the confirmed prefix is published through a monotonic counter in shared memory.
-    if (p.mode == 0 && p.dep_mode == 1) {
-      if (lane == 0) {
-        uint32_t n = 0;
-        while (sched.next(it)) {
-          if (it.type == 1) continue;
-          if (it.type == 2) spin_until(&p.counters[it.g], (uint32_t)p.M);
-          else spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
-          st_release_cta_shared(dep_count, ++n);
-        }
+    // ============================================================ scheduler (one lane)
+    // Decides the order in which this CTA runs the items it owns and feeds the other roles through the FIFO.
+    // Items of each kind are handed out through a global ticket counter (first come, first served: an SM that runs
+    // faster simply takes more of them, so all CTAs finish together); the scheduler keeps at most one claimed item per
+    // kind and decides which of them to run next:
+    //   1. the claimed P2 item, if every P1 item of its group has signalled     (unblocks the whole group's readout)
+    //   2. the claimed P3 item, if every P2 item of its group has signalled
+    //   3. the claimed P1 item, unless it is `window` or more groups ahead of the claimed P3 item (bounds the L2 footprint)
+    // An item enters the FIFO only when it is ready, so no other role ever waits on a dependency and the in-order
+    // pipeline behind the FIFO cannot deadlock: tickets are claimed in group order, P1 items never depend on anything,
+    // and a claimed-but-not-ready item never blocks the other kinds except through the window - whose P1 items all
+    // belong to later groups than the P3 item that is being waited for.
+    if (elect_one()) {
+      const long long n1tot = (long long)p.G * p.M;
+      const int n2per = p.n2_rows * p.n2_cols;
+      const long long n2tot = (long long)p.G * n2per;
+      const bool dyn = dynamic;
+      // The block mixing of a group sits on the critical path between its summaries and its readout; with np2 > 0 a few
+      // CTAs do nothing else, so a P2 item never queues behind streaming items in an in-order pipeline.
+      const int np2 = dyn ? p.np2 : 0;
+      bool has1 = true, has2 = true, has3 = true;
+      if (np2 > 0) {
+        if ((int)blockIdx.x < np2) { has1 = false; has3 = false; } else has2 = false;
       }
-    } else if (p.mode == 0) {
-      uint32_t n = 0;            // dependencies confirmed so far (warp-uniform)
-      uint32_t my_idx = lane;    // the dependency this lane is watching
-      uint32_t seen = 0;         // dependency-bearing items this lane's private schedule walk has passed
-      const uint32_t* my_ptr = nullptr;
-      uint32_t my_target = 0;
-      bool have = false;
-      auto advance_to = [&](uint32_t idx) {
-        have = false;
-        while (sched.next(it)) {
-          if (it.type == 1) continue;
-          if (seen++ == idx) {
-            my_ptr = (it.type == 2) ? &p.counters[it.g] : &p.counters[p.G + it.g];
-            my_target = (it.type == 2) ? (uint32_t)p.M : (uint32_t)(p.n2_rows * p.n2_cols);
-            have = true;
-            break;
-          }
+      if (p.mode == 1) { has2 = false; has3 = false; }
+      if (p.mode == 2) { has1 = false; has3 = false; }
+      if (p.mode == 3 || p.mode == 5) { has1 = false; has2 = false; }
+      if (p.mode == 4) has3 = false;
+      const bool dep2 = p.mode == 0 || p.mode == 4;   // P2 items wait for their group's P1 counter
+      const bool dep3 = p.mode == 0 || p.mode == 5;   // P3 items wait for their group's P2 counter
+      const bool rev3 = (p.mode == 3 || p.mode == 5) && p.reverse3;   // stand-alone readout: last groups first
+      unsigned long long* const tickets = reinterpret_cast<unsigned long long*>(p.counters + (size_t)2 * p.G * p.cnt_stride);
+      // (a short queue also keeps the tickets balanced: a CTA never hoards items it will only reach much later)
+      const uint32_t run_ahead = (uint32_t)p.run_ahead;
+      uint32_t pub = 0;
+      int ready1_g = -1, ready2_g = -1;   // groups already known to have all P1 / all P2 items done
+      auto emit = [&](int type, int g, int t) {
+        uint32_t spins = 0;
+        while (pub - ld_acquire_cta_shared(q_started) >= run_ahead) {
+          __nanosleep(32);
+          if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
         }
+        // (the slowest role is never more than a handful of items behind the producer: the ring, the two accumulators
+        //  and the staging slots bound the distance well below kFifoDepth - run_ahead)
+        *reinterpret_cast<volatile uint32_t*>(fifo + (pub & (kFifoDepth - 1))) = fifo_encode(type, g, t);
+        st_release_cta_shared(q_published, ++pub);
       };
-      advance_to(my_idx);
       uint32_t idle = 0;
+      uint32_t wg_load[2] = {0, 0};   // epilogue work handed to each warpgroup so far (arbitrary units)
+      long long cur1 = -1, cur2 = -1, cur3 = -1;   // claimed, not yet enqueued
       while (true) {
-        const bool ok = have ? (ld_acquire_gpu(my_ptr) >= my_target) : true;   // past-the-end lanes never block
-        const uint32_t mask = __ballot_sync(0xffffffffu, ok);
-        const uint32_t any_have = __ballot_sync(0xffffffffu, have);
-        const uint32_t rot = n & 31;
-        const uint32_t rmask = rot ? ((mask >> rot) | (mask << (32 - rot))) : mask;
-        const uint32_t cnt = (rmask == 0xffffffffu) ? 32u : (uint32_t)(__ffs(~rmask) - 1);
-        if (cnt > 0) {
-          if (lane == 0) st_release_cta_shared(dep_count, n + cnt);
-          if (((lane - rot) & 31) < cnt && have) { my_idx += 32; advance_to(my_idx); }
-          n += cnt;
-          idle = 0;
-        } else {
-          __nanosleep(128);
-          if (++idle > (1u << 22)) { if (lane == 0) printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+        {  // claim what is missing; the atomics are independent and overlap
+          const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0;
+          unsigned long long a1 = 0, a2 = 0, a3 = 0;
+          if (n1) a1 = atomicAdd(tickets + 0, 1ull);
+          if (n2) a2 = atomicAdd(tickets + 8, 1ull);
+          if (n3) a3 = atomicAdd(tickets + 16, 1ull);
+          if (n1) { if ((long long)a1 < n1tot) cur1 = (long long)a1; else has1 = false; }
+          if (n2) { if ((long long)a2 < n2tot) cur2 = (long long)a2; else has2 = false; }
+          if (n3) { if ((long long)a3 < n1tot) cur3 = (long long)a3; else has3 = false; }
         }
-        if (any_have == 0) break;
+        if (cur1 < 0 && cur2 < 0 && cur3 < 0) break;   // every kind is exhausted
+        const int g2 = cur2 >= 0 ? (int)(cur2 / n2per) : -1;
+        int g3 = cur3 >= 0 ? (int)(cur3 / p.M) : -1;
+        if (g3 >= 0 && rev3) g3 = p.G - 1 - g3;
+        {  // both polls are in flight together: one L2 round trip per decision
+          const bool need1 = dep2 && g2 >= 0 && g2 != ready1_g, need2 = dep3 && g3 >= 0 && g3 != ready2_g;
+          uint32_t c1 = 0, c2 = 0;
+          if (need1) c1 = ld_acquire_gpu(p.counters + (size_t)g2 * p.cnt_stride);
+          if (need2) c2 = ld_acquire_gpu(p.counters + (size_t)(p.G + g3) * p.cnt_stride);
+          if (need1 && c1 >= (uint32_t)p.M) ready1_g = g2;
+          if (need2 && c2 >= (uint32_t)n2per) ready2_g = g3;
+        }
+        const bool can2 = g2 >= 0 && (!dep2 || ready1_g == g2);
+        const bool can3 = g3 >= 0 && (!dep3 || ready2_g == g3);
+        const bool can1 = cur1 >= 0 && (p.mode != 0 || p.policy == 1 || g3 < 0 || (int)(cur1 / p.M) < g3 + p.window);
+        // Items alternate between the two epilogue warpgroups (FIFO index parity) and a P1 epilogue (normaliser) costs
+        // about twice a P3 epilogue: when both kinds are available, give the heavier one to the less loaded warpgroup
+        // instead of letting a strict P1/P3 alternation pile every P1 item onto the same warpgroup.
+        int pick = 0;
+        if (can2) pick = 2;
+        else if (can1 && p.policy == 1) pick = 1;
+        else if (can3 && can1) pick = (wg_load[pub & 1] <= wg_load[(pub & 1) ^ 1]) ? 1 : 3;
+        else if (can3) pick = 3;
+        else if (can1) pick = 1;
+        if (pick == 2) {
+          wg_load[pub & 1] += 8; emit(2, g2, (int)(cur2 % n2per)); cur2 = -1; idle = 0;
+        } else if (pick == 3) {
+          wg_load[pub & 1] += 4; emit(3, g3, (int)(cur3 % p.M)); cur3 = -1; idle = 0;
+        } else if (pick == 1) {
+          wg_load[pub & 1] += p.normalize ? 7 : 3; emit(1, (int)(cur1 / p.M), (int)(cur1 % p.M)); cur1 = -1; idle = 0;
+        } else {
+          __nanosleep(100);
+          if (++idle > (1u << 23)) { printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+        }
       }
+      emit(0, 0, 0);
     }
   } else if (warp >= 4) {
-    // ============================================================ epilogue warpgroup (TMEM -> regs -> smem -> TMA)
+    // ============================================================ epilogue warpgroups (TMEM -> regs -> smem -> global)
+    // Workspace results (S, n_loc, S~, den) leave through a swizzled staging slot and coalesced 16-byte global stores
+    // of the warpgroup itself - no TMA hand-off on the path that other CTAs are waiting for; completion is published
+    // through wg_done[wg] and turned into the group's arrival counter by the signal warp.  Only the readout tiles (O)
+    // go out by TMA (issued by thread 0 of the warpgroup, two slots in flight).
     const int q4 = warp & 3;                 // TMEM sub-partition (lanes 32*q4 .. 32*q4+31)
     const int wg = (warp - 4) >> 2;          // epilogue warpgroup: handles the items whose accumulator buffer is `wg`
     const int et = threadIdx.x - 128 - wg * kEpiThreads;   // 0..127 within the warpgroup
     ksum_s += wg * 128;
     const uint32_t bar_base = 1 + wg * 4;    // named barrier ids of this warpgroup
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    Ring r(nst);
+    uint8_t* const my_staging = staging + wg * 2 * slot_bytes;
+    Ring r(nst, wres ? p.kslabs : 0);
     uint32_t nitem = 0;
-    uint32_t nstore = 0;                     // staging buffer toggles per TMA-store chunk
+    uint32_t nchunk = 0;                     // staging chunks written so far (slot = nchunk & 1)
+    uint32_t ndone = 0;                      // workspace-producing items finished (published through wg_done[wg])
+    int last_tma_slot = -1;                  // slot read by the most recent TMA store of this warpgroup (thread 0's view)
     uint32_t v[32];
     const bool prof_on = p.prof != nullptr && et == 0 && wg == 0;
-    long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0;
-    uint32_t ndep_e = 0;                     // dependency-bearing (P2/P3) items seen so far
+    long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_ld = 0, t_out = 0, t_pack = 0, t_stage = 0;
 
     // write one [rows][128 B] chunk row into the swizzle-128B staging tile
     auto stage_row = [&](uint8_t* buf, int row, const uint32_t* w32) {
+      const long long t0 = prof_on ? clock64() : 0;
       uint4* dst = reinterpret_cast<uint4*>(buf + row * 128);
 #pragma unroll
       for (int c = 0; c < 8; ++c)
         dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
+      if (prof_on) t_stage += clock64() - t0;
     };
-    // Staging hand-off with the store warp.  Warpgroup `wg` owns two 16 KB slots; the chunks of an item are written
-    // alternately into them and handed over two at a time (one mbarrier round trip per pair - the round trip, not
-    // the copy, is what costs ~1500 cycles).  cj = chunk index within the item, nch = chunks of the item.
-    int cj = 0, nch = 0;
-    auto staging_acquire = [&]() -> uint8_t* {
-      if ((cj & 1) == 0) mbar_wait_prof(&sfree[wg], (nstore & 1) ^ 1, prof_on, w_sfree);   // first use passes immediately
-      return staging + wg * 2 * slot_bytes + (cj & 1) * slot_bytes;
-    };
-    auto staging_publish = [&]() {
-      fence_proxy_async_smem();                 // my rows -> visible to the async proxy (TMA)
-      ++cj;
-      if ((cj & 1) == 0 || cj == nch) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sfull[wg]);   // one arrival per epilogue warp
-        ++nstore;
+    // next staging slot; a TMA store that is still reading it (issued two chunks ago) must have finished
+    auto slot_acquire = [&]() -> uint8_t* {
+      const int s_ = (int)(nchunk & 1);
+      const long long t0 = prof_on ? clock64() : 0;
+      if (et == 0 && last_tma_slot >= 0) {
+        if (last_tma_slot == s_) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
       }
+      named_bar_sync(bar_base + 1, kEpiThreads);
+      if (prof_on) w_sfree += clock64() - t0;
+      return my_staging + s_ * slot_bytes;
+    };
+    // rows of the slot are complete: copy [nrows][128 B] to global memory, row r to gbase + r * row_stride (bytes)
+    auto chunk_copy = [&](const uint8_t* buf, uint8_t* gbase, size_t row_stride, int nrows, int nvalid) {
+      named_bar_sync(bar_base, kEpiThreads);
+      const long long t0 = prof_on ? clock64() : 0;
+      // thread -> (row = k * 16 + et / 8, 16-byte piece et % 8): a warp instruction covers 4 rows x 128 contiguous bytes
+      const int c = et & 7, r0_ = et >> 3;
+      const uint8_t* sp = buf + r0_ * 128 + ((c ^ (r0_ & 7)) << 4);   // (k * 16 + r0_) & 7 == r0_ & 7
+      uint8_t* gp = gbase + (size_t)r0_ * row_stride + c * 16;
+      auto run = [&](auto KN) {
+        constexpr int kn = decltype(KN)::value;
+        uint4 val[kn];
+#pragma unroll
+        for (int k = 0; k < kn; ++k) val[k] = *reinterpret_cast<const uint4*>(sp + k * 16 * 128);
+#pragma unroll
+        for (int k = 0; k < kn; ++k)
+          if (k * 16 + r0_ < nvalid) __stcg(reinterpret_cast<uint4*>(gp + (size_t)k * 16 * row_stride), val[k]);
+      };
+      if (nrows == 64) run(std::integral_constant<int, 4>{}); else run(std::integral_constant<int, 8>{});
+      if (prof_on) t_out += clock64() - t0;
+      ++nchunk;
+    };
+    // rows of the slot are complete: thread 0 sends it with TMA
+    auto chunk_tma_begin = [&]() { fence_proxy_async_smem(); named_bar_sync(bar_base, kEpiThreads); };
+    auto chunk_tma_end = [&]() {
+      if (et == 0) { tma_store_commit(); last_tma_slot = (int)(nchunk & 1); }
+      ++nchunk;
+    };
+    // every global store of this item has been issued by all 128 threads: publish
+    auto item_done = [&]() {
+      named_bar_sync(bar_base + 3, kEpiThreads);
+      ++ndone;
+      if (et == 0) st_release_cta_shared(&wg_done[wg], ndone);
     };
     // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
     auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
       uint32_t v2[32];
+      const long long t0 = prof_on ? clock64() : 0;
       tmem_ld_x32(taddr, v);
       tmem_ld_x32(taddr + 32, v2);
       tmem_ld_wait();
+      if (prof_on) t_ld += clock64() - t0;
 #pragma unroll
       for (int e = 0; e < 16; ++e) {
         const float a = __uint_as_float(v[2 * e]) * scale, bq = __uint_as_float(v[2 * e + 1]) * scale;
@@ -589,6 +746,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           pk[e] = pack_bf16x2(a, bq); pk[16 + e] = pack_bf16x2(c2, d2);
         }
       }
+      if (prof_on) t_pack += clock64() - t0;
     };
     // x = hi + lo with hi, lo in the 16-bit I/O type
     auto split16 = [&](float x, uint16_t& hi, uint16_t& lo) {
@@ -621,25 +779,16 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       return acc_n;
     };
 
-    while (sched.next(it)) {
+    while (sched.next_warp(it, lane)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
-      if ((int)ab != wg) {   // the other warpgroup's item: only keep the ring / dependency bookkeeping in step
-        r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? 2 * p.kslabs : p3_stages<D>(p)));
-        if (it.type != 1) ++ndep_e;
+      if ((int)ab != wg) {   // the other warpgroup's item: only keep the ring bookkeeping in step
+        r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? (wres ? 1 : 2) * p.kslabs : p3_stages<D>(p)));
         ++nitem;
         continue;
       }
       const long long t_item = prof_on ? clock64() : 0;
       if (et == 0) trace_ev(p, 2, nitem, 0);
-      cj = 0;
-      if (it.type == 1) nch = (p.normalize ? 1 : 0) + D / 64;
-      else if (it.type == 3) nch = p.nsub * (D / 64);
-      else {
-        const int tcx = it.t % p.n2_cols;
-        nch = 4;
-        if (tcx >= p.n2_scols) { const int rem = (2 * p.wpad - (tcx - p.n2_scols) * 256 + 31) / 32; nch = rem < 8 ? rem : 8; }
-      }
       if (it.type == 1) {
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) trace_ev(p, 2, nitem, 1);
@@ -648,6 +797,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         const bool row_ok = (D == 128) || (lane < 16);
         const int row = (D == 128) ? et : (q4 * 16 + (lane & 15));
         const int kvs = (D == 64 ? 1 : 2) + p.ropenorm;
+        const size_t blk = (size_t)it.g * p.M + it.t;
+        uint16_t* const srow = p.ws_S + blk * p.ncols;
         r.advance(p.nsub * kvs);
         if (p.normalize) {
           // ---- n_loc first: it frees the Q stage(s) of the ring early
@@ -656,23 +807,23 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           tmem_ld_wait();
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
           named_bar_sync(bar_base + 2, kEpiThreads);  // ksum_s complete
-          uint16_t* nbuf = reinterpret_cast<uint16_t*>(staging_acquire());   // [hi: wpad][lo: wpad] -> one bulk store
+          uint16_t* const nbuf = srow + D * D;        // [hi: wpad][lo: wpad]
           if constexpr (D == 64) {
-            mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_q);
-            const uint8_t* qs = ring + r.stage * kStageBytes;
+            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_q);
+            const uint8_t* qs = ring + r.idx() * kStageBytes;
             for (int t = et; t < p.wpad; t += kEpiThreads) {
               uint16_t hi, lo;
               split16(dot_row64(qs, t, ksum_s, 0.f), hi, lo);
               nbuf[t] = hi;
               nbuf[p.wpad + t] = lo;
             }
-            named_bar_sync(bar_base, kEpiThreads);
-            if (et == 0) mbar_arrive(&empty[r.stage]);
+            named_bar_sync(bar_base + 2, kEpiThreads);
+            if (et == 0) mbar_arrive(&empty[r.idx()]);
             r.advance();
           } else {
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait_prof(&full[r.stage], r.phase, prof_on, w_q);
-              const uint8_t* qs = ring + r.stage * kStageBytes;
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_q);
+              const uint8_t* qs = ring + r.idx() * kStageBytes;
               if (et < p.TW) {
                 const int t = sub * p.TW + et;
                 float a = dot_row64(qs, et, ksum_s, 0.f);
@@ -682,25 +833,27 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
                 nbuf[t] = hi;
                 nbuf[p.wpad + t] = lo;
               }
-              named_bar_sync(bar_base, kEpiThreads);
-              if (et == 0) mbar_arrive(&empty[r.stage]);
+              named_bar_sync(bar_base + 2, kEpiThreads);
+              if (et == 0) mbar_arrive(&empty[r.idx()]);
               r.advance();
             }
           }
-          staging_publish();
         }
         for (int c = 0; c < D / 64; ++c) {
           uint32_t pk[32];
           load_pack64(acc + c * 64, 1.0f, pk);
-          uint8_t* buf = staging_acquire();
+          uint8_t* buf = slot_acquire();
           if (row_ok) stage_row(buf, row, pk);
-          staging_publish();
+          chunk_copy(buf, reinterpret_cast<uint8_t*>(srow) + c * 128, (size_t)D * 2, D, D);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
+        item_done();
       } else if (it.type == 2) {
-        const int tc = it.t % p.n2_cols;
+        const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+        const int nvalid = p.M - ti * 128;       // rows of this tile inside the matrix (TMA used to clip them)
+        const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
@@ -708,42 +861,36 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
             load_pack64(acc + c * 64, 1.0f, pk);
-            uint8_t* buf = staging_acquire();
+            uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
-            staging_publish();
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
+                       (size_t)D * D * 2, 128, nvalid);
           }
         } else {
           for (int q = 0; q < 8; ++q) {
-            if ((tc - p.n2_scols) * 256 + q * 32 >= 2 * p.wpad) break;   // uniform: nothing left in this tile
+            const int col0 = (tc - p.n2_scols) * 256 + q * 32;
+            if (col0 >= 2 * p.wpad) break;   // uniform: nothing left in this tile
             tmem_ld_x32(acc + q * 32, v);
             tmem_ld_wait();
-            uint8_t* buf = staging_acquire();
+            uint8_t* buf = slot_acquire();
             stage_row(buf, et, v);
-            staging_publish();
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(const_cast<float*>(p.den) + row0 * (size_t)(2 * p.wpad) + col0),
+                       (size_t)2 * p.wpad * 4, 128, nvalid);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        r.advance(2 * p.kslabs);
+        r.advance((wres ? 1 : 2) * p.kslabs);
+        item_done();
       } else {
         const int i = it.t;
+        const int b = it.g / p.H, h = it.g % p.H;
         float dsum[2] = {1.f, 1.f};
         if (p.normalize) {
-          // den = mix.n_loc_hi + mix.n_loc_lo + eps was written by other CTAs.  Once the dependency warp has confirmed
-          // this item's group (monotonic smem counter - NOT the ring barriers, whose phase may already have wrapped
-          // because P3 stages are recycled by the MMA warp alone), den is visible: fetch it through L2 now and let the
-          // latency overlap the wait for the accumulator.
-          if (p.mode == 0) {
-            if (lane == 0) {     // one poller per warp: 128 threads spinning on one smem word would starve the banks
-              uint32_t spins = 0;
-              while (ld_acquire_cta_shared(dep_count) <= ndep_e) {
-                __nanosleep(32);
-                if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: epilogue dep wait timed out (block %d)\n", blockIdx.x); __trap(); }
-              }
-            }
-            __syncwarp();
-          }
+          // den = mix.n_loc_hi + mix.n_loc_lo + eps was written by other CTAs; the item was only enqueued after its
+          // group's P2 counter had been acquired, so it is visible: fetch it through L2 now and let the latency overlap
+          // the wait for the accumulator.
           const float* dg = p.den + (size_t)(it.g * p.M + i) * (2 * p.wpad);
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
@@ -761,9 +908,11 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
             load_pack64(acc + sub * 128 + c * 64, rden, pk);
-            uint8_t* buf = staging_acquire();
+            uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
-            staging_publish();
+            chunk_tma_begin();
+            if (et == 0) tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, i, h, b);
+            chunk_tma_end();
           }
         }
         tc_fence_before();
@@ -771,7 +920,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         if (lane == 0) mbar_arrive(&tempty[ab]);
         r.advance(p3_stages<D>(p));
       }
-      if (it.type != 1) ++ndep_e;
       if (et == 0) trace_ev(p, 2, nitem, 2);
       if (prof_on) {
         const long long dt = clock64() - t_item;
@@ -779,150 +927,39 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
       ++nitem;
     }
+    if (et == 0) tma_store_wait_all<0>();
     if (prof_on) {
       unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
       pr[5] = (unsigned long long)w_tfull; pr[6] = (unsigned long long)w_sfree; pr[7] = (unsigned long long)w_q;
       pr[8] = (unsigned long long)t_p1; pr[9] = (unsigned long long)t_p2; pr[10] = (unsigned long long)t_p3;
       pr[11] = nitem;
+      pr[12] = (unsigned long long)t_ld; pr[13] = (unsigned long long)t_out;
+      pr[7] = (unsigned long long)t_pack; pr[15] = (unsigned long long)t_stage;
     }
   } else if (warp == 3) {
-    // ============================================================ store / signal warp (one lane)
-    // Issues every TMA store (so the bulk async-groups belong to this thread), recycles the staging buffers and
-    // publishes the per-group dependency counters once an item's stores have fully completed - none of this sits on
-    // the epilogue warps' critical path.
-    if (elect_one()) {
-      uint32_t k = 0;              // bulk groups committed so far
-      const bool prof_on = p.prof != nullptr;
-      long long w_sfull = 0, w_done = 0;
-      // Completion signals are deferred instead of draining the store queue after every item: bulk groups retire in
-      // order, so once kSigLag younger groups have been committed, `wait_group kSigLag` (normally already satisfied)
-      // proves the item's bytes are in global memory.  Whenever the warp would idle it flushes everything pending, so
-      // a signal never waits on work that (transitively) depends on it.
-      constexpr int kSigLag = 1, kMaxPending = 8;
-      uint32_t* pend_ptr[kMaxPending] = {};
-      uint32_t pend_seq[kMaxPending] = {};
-      int pend_head = 0, pend_n = 0;
-      auto fire = [&](uint32_t upto_seq) {     // publish every pending signal whose last group index is <= upto_seq
-        bool fenced = false;
-        while (pend_n > 0 && pend_seq[pend_head] <= upto_seq) {
-          if (!fenced) { fence_proxy_async_all(); __threadfence(); fenced = true; }
-          red_release_gpu_add(pend_ptr[pend_head], 1u);
-          pend_head = (pend_head + 1) % kMaxPending;
-          --pend_n;
-        }
-      };
-      uint32_t kw[2] = {0, 0};   // chunks taken from each warpgroup's staging buffer
-      int cur = 0;               // warpgroup (= item parity) of the item being stored
-      int unfreed = -1;          // warpgroup whose previous hand-off has been issued but not yet handed back
-      auto drain_all = [&]() {
-        const long long t0 = prof_on ? clock64() : 0;
-        tma_store_wait_all<0>();
-        if (unfreed >= 0) { mbar_arrive(&sfree[unfreed]); unfreed = -1; }
-        fire(k);
-        if (prof_on) w_done += clock64() - t0;
-      };
-      int cj = 0, nch = 0;       // chunk index within the item / chunks of the item (same rule as the epilogue)
-      auto take = [&]() -> uint8_t* {
-        if ((cj & 1) == 0) {
-          if (pend_n > 0 && !mbar_try_wait(&sfull[cur], kw[cur] & 1)) drain_all();   // idle: flush the signals
-          mbar_wait_prof(&sfull[cur], kw[cur] & 1, prof_on, w_sfull);
-          ++kw[cur];
-        }
-        return staging + cur * 2 * slot_bytes + (cj & 1) * slot_bytes;
-      };
-      // Buffers are handed back lazily: the TMA store engine drains a 32 KB pair in ~2000 cycles, so blocking on every
-      // read-out would make this lane the bottleneck.  After committing hand-off k we only wait until hand-off k-1 has
-      // been read (`wait_group.read 1`) - unless the same warpgroup produces the next hand-off too (an item with more
-      // than two chunks), in which case its slots must come back before it can continue.
-      auto issued = [&]() {
-        ++cj;
-        if ((cj & 1) != 0 && cj != nch) return;   // second chunk of the pair still to come
-        tma_store_commit();
-        ++k;
-        if (cj != nch) {                       // more hand-offs of this item follow from the same warpgroup
-          tma_store_wait_read<0>();
-          if (unfreed >= 0) { mbar_arrive(&sfree[unfreed]); unfreed = -1; }
-          mbar_arrive(&sfree[cur]);
-        } else {
-          tma_store_wait_read<1>();            // everything but the newest group has been read out of smem
-          if (unfreed >= 0) mbar_arrive(&sfree[unfreed]);
-          unfreed = cur;
-        }
-        if (pend_n > 0 && k >= pend_seq[pend_head] + kSigLag) {
-          tma_store_wait_all<kSigLag>();       // groups 1..k-kSigLag are complete
-          fire(k - kSigLag);
-        }
-      };
-      uint32_t sitem = 0;
+    // ============================================================ signal warp (one lane)
+    // Turns "warpgroup finished item n" (wg_done, shared memory) into the group's arrival counter in global memory.
+    // The release (gpu scope) orders every global store of the warpgroup's 128 threads before the increment: they
+    // happen before the warpgroup's named barrier, thread 0's st.release.cta and this lane's ld.acquire.cta.  The
+    // ~1 us the release takes under load is spent here, not in the epilogue.
+    if (dynamic && elect_one()) {
+      uint32_t seen[2] = {0, 0};
+      uint32_t n = 0;
       while (sched.next(it)) {
-        cur = (int)(sitem & 1);
-        cj = 0;
-        if (it.type == 1) nch = (p.normalize ? 1 : 0) + D / 64;
-        else if (it.type == 3) nch = p.nsub * (D / 64);
-        else {
-          const int tcx = it.t % p.n2_cols;
-          nch = 4;
-          if (tcx >= p.n2_scols) { const int rem = (2 * p.wpad - (tcx - p.n2_scols) * 256 + 31) / 32; nch = rem < 8 ? rem : 8; }
-        }
-        trace_ev(p, 3, sitem, 0);
-        if (it.type == 1) {
-          const int row = it.g * p.M + it.t;
-          if (p.normalize) {
-            uint8_t* buf = take();
-            bulk_store_1d(p.ws_S + (size_t)row * p.ncols + D * D, buf, (uint32_t)(4 * p.wpad));
-            issued();
+        const int wgi = (int)(n & 1);
+        trace_ev(p, 3, n, 0);
+        if (it.type != 3) {
+          ++seen[wgi];
+          uint32_t spins = 0;
+          while (ld_acquire_cta_shared(&wg_done[wgi]) < seen[wgi]) {
+            __nanosleep(32);
+            if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: signal wait timed out (block %d)\n", blockIdx.x); __trap(); }
           }
-          for (int c = 0; c < D / 64; ++c) {
-            uint8_t* buf = take();
-            tma_store_3d(&p.tmSst, buf, c * 64, 0, row);
-            issued();
-          }
-        } else if (it.type == 2) {
-          const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
-          if (tc < p.n2_scols) {
-            for (int c = 0; c < 4; ++c) {
-              uint8_t* buf = take();
-              tma_store_3d(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g);
-              issued();
-            }
-          } else {
-            for (int q = 0; q < 8; ++q) {
-              if ((tc - p.n2_scols) * 256 + q * 32 >= 2 * p.wpad) break;
-              uint8_t* buf = take();
-              tma_store_3d(&p.tmDen, buf, (tc - p.n2_scols) * 256 + q * 32, ti * 128, it.g);
-              issued();
-            }
-          }
-        } else {
-          const int b = it.g / p.H, h = it.g % p.H;
-          for (int sub = 0; sub < p.nsub; ++sub)
-            for (int c = 0; c < D / 64; ++c) {
-              uint8_t* buf = take();
-              tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, it.t, h, b);
-              issued();
-            }
+          trace_ev(p, 3, n, 1);
+          red_release_gpu_add(p.counters + (size_t)((it.type == 1 ? 0 : p.G) + it.g) * p.cnt_stride, 1u);
         }
-        trace_ev(p, 3, sitem, 1);
-        if (p.mode == 0 && it.type != 3 && p.sig_mode == 1) {
-          tma_store_wait_all<0>();
-          fence_proxy_async_all();
-          __threadfence();
-          red_release_gpu_add(&p.counters[(it.type == 1 ? 0 : p.G) + it.g], 1u);
-        } else if (p.mode == 0 && it.type != 3) {
-          if (pend_n == kMaxPending) drain_all();
-          const int slot = (pend_head + pend_n) % kMaxPending;
-          pend_ptr[slot] = &p.counters[(it.type == 1 ? 0 : p.G) + it.g];
-          pend_seq[slot] = k;                  // the item's last group
-          ++pend_n;
-        }
-        trace_ev(p, 3, sitem, 2);
-        ++sitem;
-      }
-      drain_all();
-      tma_store_wait_all<0>();
-      if (prof_on) {
-        unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
-        pr[12] = (unsigned long long)w_sfull; pr[13] = (unsigned long long)w_done;
+        trace_ev(p, 3, n, 2);
+        ++n;
       }
     }
   }
@@ -930,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[1] = t; }
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 

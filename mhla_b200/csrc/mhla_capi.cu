@@ -75,6 +75,7 @@ bool encode_map(CUtensorMap* out, const MapSpec& s) {
 }
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (separate L2 sectors)
 
 // ------------------------------------------------------------------------------------------------ blockmix
 struct BlockmixPlan {
@@ -88,6 +89,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   if (d->B < 1 || d->H < 1 || d->M < 1 || d->w < 1) return MHLA_ERR_UNSUPPORTED_SHAPE;
   if (d->D != 64 && d->D != 128) return MHLA_ERR_UNSUPPORTED_SHAPE;
   if (d->w > 256) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if ((long long)d->B * d->H > 16383 || d->M > 65535) return MHLA_ERR_UNSUPPORTED_SHAPE;   // item FIFO field widths
   const int D = d->D;
   pl->G = d->B * d->H;
   pl->TW = d->w >= 128 ? 128 : (d->w + 15) / 16 * 16;
@@ -107,7 +109,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->off_St = off;  off = align_up(off + GM * D * D * 2, 1024);
   pl->off_den = off; off = align_up(off + GM * (pl->wpad ? 2 * pl->wpad : 32) * 4, 1024);
   pl->off_W = off;   off = align_up(off + (size_t)2 * d->M * pl->Mp * 2, 1024);
-  pl->off_cnt = off; off = align_up(off + (size_t)2 * pl->G * 4, 1024);
+  pl->off_cnt = off; off = align_up(off + ((size_t)2 * pl->G * kCntStride + 64) * 4, 1024);   // + 3 item tickets
   pl->total = off;
   return MHLA_OK;
 }
@@ -198,13 +200,14 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
     if (!encode_map(&P->tmStld, s)) return MHLA_ERR_CUDA;
   }
   P->ws_S = S;
+  P->ws_St = reinterpret_cast<uint16_t*>(St);
   P->den = den;
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
   P->G = pl.G; P->H = d->H; P->M = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
   P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
   P->normalize = pl.normalize; P->ropenorm = pl.ropenorm; P->is_fp16 = d->dtype == MHLA_FP16;
-  P->mode = 0; P->lag2 = 1; P->lag3 = 3;
+  P->mode = 0; P->window = 8; P->run_ahead = 2; P->cnt_stride = kCntStride;
   P->eps = d->eps;
   (void)Wp;
   return MHLA_OK;
@@ -292,11 +295,21 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   }
 
   P.prof = g_prof_buffer;
-  P.dep_mode = 0; P.sig_mode = 0;
-  if (const char* e = std::getenv("MHLA_DEPMODE")) P.dep_mode = std::atoi(e);
+  P.sig_mode = 0;
   if (const char* e = std::getenv("MHLA_SIGMODE")) P.sig_mode = std::atoi(e);
-  if (const char* e = std::getenv("MHLA_LAG2")) P.lag2 = std::atoi(e);   // tuning knobs (schedule distance, in groups,
-  if (const char* e = std::getenv("MHLA_LAG3")) P.lag3 = std::atoi(e);   // between the phases of one (b,h) group)
+  if (const char* e = std::getenv("MHLA_WINDOW")) P.window = std::atoi(e);       // tuning knobs of the fused kernel's
+  if (const char* e = std::getenv("MHLA_RUNAHEAD")) P.run_ahead = std::atoi(e);  // run-time scheduler
+  P.np2 = -1;
+  P.trace_cta = 0;
+  P.policy = 0;
+  if (const char* e = std::getenv("MHLA_POLICY")) P.policy = std::atoi(e);
+  P.pf_dist = 0;
+  if (const char* e = std::getenv("MHLA_PF")) P.pf_dist = std::atoi(e);
+  if (const char* e = std::getenv("MHLA_TRACE_CTA")) P.trace_cta = std::atoi(e);
+  if (const char* e = std::getenv("MHLA_NP2")) P.np2 = std::atoi(e);
+  if (P.window < 1) P.window = 1;
+  if (P.run_ahead < 1) P.run_ahead = 1;
+  if (P.run_ahead > 16) P.run_ahead = 16;
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
   bool& attr = d->D == 64 ? g_attr_set64 : g_attr_set128;
   if (!attr) {
@@ -310,7 +323,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   int launches = 0;
   mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mix, (long long)d->mix_ld,
                                                reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp, 0, 1.0f,
-                                               d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
+                                               d->dtype == MHLA_FP16, P.counters, 2 * pl.G * kCntStride + 64);
   ++launches;
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
   auto launch_pdl = [&](int grid) -> bool {
@@ -330,15 +343,26 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
     int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
     if (d->flags & MHLA_FLAG_ONLY_P2) first = last = 2;
+    // Default: two launches chained with PDL - summaries + block mixing in one dynamically scheduled kernel (mode 4:
+    // the mixing of a group starts as soon as its summaries are complete and overlaps the streaming of later groups),
+    // then the readout with the groups walked backwards (the Q tiles the normaliser read last are still in L2).
+    // MHLA_FLAG_UNFUSED and the debugging flags select the plain phase-by-phase launches instead.
+    const bool two_launch = first == 1 && last == 3 && !(d->flags & MHLA_FLAG_UNFUSED) && !std::getenv("MHLA_THREE_LAUNCH");
+    P.reverse3 = two_launch ? 1 : 0;
+    if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     for (int mode = first; mode <= last; ++mode) {
-      P.mode = mode;
+      if (two_launch && mode == 2) continue;
+      P.mode = (two_launch && mode == 1) ? 4 : ((two_launch && mode == 3) ? 5 : mode);
       // P1 with D = 64 only stages 1 KB (n_loc) + 8 KB (S) per item: give the ring a sixth stage instead (a multiple
       // of the 3 stages per item keeps the long-lived Q stage out of the K/V recycling path)
-      const bool small_staging = (mode == 1 && d->D == 64);
+      const bool small_staging = (P.mode == 1 && d->D == 64);
       P.slot_bytes = small_staging ? 8192 : 16384;
       P.ring_stages = small_staging ? 6 : 5;
-      const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
+      if (P.mode == 4 && P.np2 < 0) P.np2 = 0;
+      const long long items = (long long)pl.G * (P.mode == 4 ? n1 + n2 : (mode == 1 ? n1 : (mode == 2 ? n2 : n3)));
+      if (P.mode != 4 && P.mode != 0) P.np2 = 0;
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+      if (P.np2 > grid / 2) P.np2 = grid / 2;
       if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
       ++launches;
     }
@@ -348,6 +372,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     P.ring_stages = 5;
     const long long items = (long long)pl.G * (n1 + n2 + n3);
     const int grid = (int)(items < g_num_sms ? items : g_num_sms);
+    // dedicated block-mixing CTAs: one per P2 tile of a group, when that leaves most of the grid for streaming
+    if (P.np2 < 0) P.np2 = (n2 * 4 <= grid) ? (int)n2 : 0;
+    if (P.np2 > grid / 2) P.np2 = grid / 2;
     if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
     ++launches;
   }

@@ -64,7 +64,7 @@ def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
 
 def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                   out: Optional[torch.Tensor] = None, fused: bool = False, unfused: Optional[bool] = None,
-                  debug_flags: int = 0) -> torch.Tensor:
+                  three_launch: bool = False, debug_flags: int = 0) -> torch.Tensor:
     """Non-causal block-mixed MHLA forward on block-major tensors.
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
@@ -103,7 +103,8 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     d.dtype = _DT[cdtype]
     if unfused is not None:          # legacy spelling used by the tests: unfused=False -> the single fused kernel
         fused = not unfused
-    d.flags = (_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_FUSED if fused else 0) | int(debug_flags)
+    d.flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_FUSED if fused else 0) |
+               (_capi.FLAG_UNFUSED if three_launch else 0) | int(debug_flags))
     d.eps = float(eps)
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)

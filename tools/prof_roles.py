@@ -11,6 +11,10 @@ import mhla_b200  # noqa: E402
 from mhla_b200 import _capi  # noqa: E402
 
 normalize = "--no-normalize" not in sys.argv
+KW = dict(fused=True)
+for m, f in (("--p1only", _capi.FLAG_STOP_AFTER_P1), ("--p2only", _capi.FLAG_ONLY_P2), ("--p3only", _capi.FLAG_ONLY_P3)):
+    if m in sys.argv:
+        KW = dict(debug_flags=f)
 B, H, M, w, D = 2, 16, 128, 256, 64
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)
@@ -22,20 +26,20 @@ out = torch.empty_like(q)
 L = _capi.lib()
 L.mhla_debug_set_profile_buffer.argtypes = [C.c_void_p]
 for _ in range(3):
-    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=True)
+    mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **KW)
 torch.cuda.synchronize()
 prof = torch.zeros(148, 16, dtype=torch.int64, device=dev)
 L.mhla_debug_set_profile_buffer(prof.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
-mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=True)
+mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **KW)
 e1.record()
 torch.cuda.synchronize()
 L.mhla_debug_set_profile_buffer(None)
 p = prof.cpu().double()
 names = ["prod.wait_empty", "prod.wait_dep", "prod.total", "mma.wait_full", "mma.wait_tempty", "epi.wait_tfull",
-         "epi.wait_sfree", "epi.wait_qfull", "epi.t_P1", "epi.t_P2", "epi.t_P3", "epi.items", "store.wait_sfull",
-         "store.wait_done"]
+         "epi.wait_sfree", "epi.t_ld+pack", "epi.t_P1", "epi.t_P2", "epi.t_P3", "epi.items", "epi.t_tmem_ld",
+         "epi.t_copy", "gt", "epi.t_stage"]
 print(f"normalize={normalize}  step (events) = {e0.elapsed_time(e1) * 1e3:.1f} us")
 print("SM clock (GHz) from clock64/globaltimer over the producer lifetime: mean %.3f min %.3f max %.3f ; lifetime us mean %.1f" % ((p[:,2]/p[:,14]).mean(), (p[:,2]/p[:,14]).min(), (p[:,2]/p[:,14]).max(), p[:,14].mean()/1e3))
 tot = p[:, 2].mean()

@@ -13,6 +13,9 @@ struct P {
   CUtensorMap tm;
   long long nboxes;   // total boxes in the tensor
   int boxes_per_stage, nstages, box_rows, hold_cycles;
+  CUtensorMap tmo;    // output tensor (TMA stores)
+  int store_every;    // consumer stores the stage's first box back after every `store_every`-th stage (0: never)
+  long long wrap;     // stage units wrap modulo this (small value: the stream is served from L2)
 };
 
 __global__ void __launch_bounds__(128) stream_kernel(const __grid_constant__ P p) {
@@ -31,19 +34,28 @@ __global__ void __launch_bounds__(128) stream_kernel(const __grid_constant__ P p
     for (long long u = blockIdx.x; u < nst; u += gridDim.x) {
       mbar_wait(&empty[st], ph ^ 1);
       mbar_arrive_expect_tx(&full[st], stage_bytes);
+      const long long uu = p.wrap ? (u % p.wrap) : u;
       for (int b = 0; b < p.boxes_per_stage; ++b)
         tma_load_2d(smem + st * stage_bytes + b * box_bytes, &p.tm, &full[st], 0,
-                    (int)((u * p.boxes_per_stage + b) * p.box_rows), kEvictFirst);
+                    (int)((uu * p.boxes_per_stage + b) * p.box_rows), p.wrap ? kEvictLast : kEvictFirst);
       if (++st == p.nstages) { st = 0; ph ^= 1; }
     }
   } else if (threadIdx.x == 32) {
-    int st = 0; uint32_t ph = 0;
+    int st = 0; uint32_t ph = 0; long long n = 0;
     for (long long u = blockIdx.x; u < nst; u += gridDim.x) {
       mbar_wait(&full[st], ph);
       if (p.hold_cycles) { const long long t0 = clock64(); while (clock64() - t0 < p.hold_cycles) {} }
+      if (p.store_every && (n++ % p.store_every) == 0) {
+        fence_proxy_async_smem();
+        for (int b = 0; b < p.boxes_per_stage; ++b)
+          tma_store_2d(&p.tmo, smem + st * stage_bytes + b * box_bytes, 0, (int)((u * p.boxes_per_stage + b) * p.box_rows));
+        tma_store_commit();
+        tma_store_wait_read<0>();
+      }
       mbar_arrive(&empty[st]);
       if (++st == p.nstages) { st = 0; ph ^= 1; }
     }
+    tma_store_wait_all<0>();
   }
 }
 
@@ -63,11 +75,17 @@ int main() {
   cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  struct Cfg { int box_rows, boxes_per_stage, nstages, ctas_per_sm, hold; };
+  void* obuf;
+  cudaMalloc(&obuf, bytes);
+  struct Cfg { int box_rows, boxes_per_stage, nstages, ctas_per_sm, hold, grid, store_every, l2_mb; };
   const Cfg cfgs[] = {
-      {128, 2, 6, 1, 0}, {128, 2, 3, 1, 0}, {128, 2, 2, 1, 0}, {128, 1, 12, 1, 0}, {128, 4, 3, 1, 0},
-      {256, 1, 6, 1, 0}, {64, 4, 6, 1, 0}, {128, 2, 3, 2, 0}, {128, 1, 6, 2, 0}, {128, 1, 4, 3, 0},
-      {128, 2, 6, 1, 1500}, {128, 2, 6, 1, 3000},
+      {128, 2, 6, 1, 0, 148, 0, 0},  {128, 2, 5, 1, 0, 148, 0, 0},  {128, 2, 5, 1, 0, 130, 0, 0}, {128, 2, 5, 1, 0, 112, 0, 0},
+      {128, 2, 5, 1, 0, 74, 0, 0},   {128, 2, 5, 1, 0, 37, 0, 0},   {128, 2, 5, 1, 0, 8, 0, 0},   {128, 2, 5, 1, 0, 1, 0, 0},
+      {128, 2, 5, 1, 1500, 148, 0, 0}, {128, 2, 5, 1, 3000, 148, 0, 0}, {128, 2, 3, 1, 1500, 148, 0, 0},
+      {128, 2, 5, 1, 0, 148, 4, 0},  {128, 2, 5, 1, 0, 148, 3, 0},  {128, 2, 5, 1, 0, 148, 2, 0},  {128, 2, 5, 1, 0, 148, 1, 0},
+      {128, 2, 5, 1, 0, 112, 3, 0},
+      {128, 2, 5, 1, 0, 148, 0, 32}, {128, 2, 5, 1, 0, 112, 0, 32}, {128, 2, 5, 1, 0, 18, 0, 32},  {128, 2, 5, 1, 0, 1, 0, 32},
+      {128, 2, 2, 1, 0, 148, 0, 32}, {128, 2, 5, 1, 0, 148, 3, 32},
   };
   for (const Cfg& c : cfgs) {
     P p;
@@ -81,8 +99,12 @@ int main() {
     if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); return 1; }
     p.nboxes = rows / c.box_rows;
     p.boxes_per_stage = c.boxes_per_stage; p.nstages = c.nstages; p.box_rows = c.box_rows; p.hold_cycles = c.hold;
+    enc(&p.tmo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, obuf, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    p.store_every = c.store_every;
+    p.wrap = c.l2_mb ? ((long long)c.l2_mb << 20) / (c.box_rows * 128 * c.boxes_per_stage) : 0;
     const int smem = c.box_rows * 128 * c.boxes_per_stage * c.nstages;
-    const int grid = sms * c.ctas_per_sm;
+    const int grid = c.grid * c.ctas_per_sm;
     float best = 1e9f;
     for (int it = 0; it < 4; ++it) {
       cudaEventRecord(e0);
@@ -93,8 +115,10 @@ int main() {
       float ms; cudaEventElapsedTime(&ms, e0, e1);
       if (ms < best) best = ms;
     }
-    printf("box %3d rows x128B, %d boxes/stage, %2d stages (%3d KB smem), %d CTA/SM, hold %4d cyc: %7.1f us  %7.1f GB/s\n",
-           c.box_rows, c.boxes_per_stage, c.nstages, smem / 1024, c.ctas_per_sm, c.hold, best * 1e3, bytes / (best * 1e-3) / 1e9);
+    const double wr = c.store_every ? (double)bytes / c.store_every : 0.0;
+    printf("box %3d x128B, %d boxes/stage, %2d stages, grid %3d, hold %4d cyc, store 1/%d, src %s: %7.1f us  read %7.1f GB/s  read+write %7.1f GB/s  (%.1f B/clk/SM @1.9GHz)\n",
+           c.box_rows, c.boxes_per_stage, c.nstages, grid, c.hold, c.store_every, c.l2_mb ? "L2 " : "HBM", best * 1e3,
+           bytes / (best * 1e-3) / 1e9, (bytes + wr) / (best * 1e-3) / 1e9, (bytes + wr) / (best * 1e-3) / grid / 1.9e9);
   }
   return 0;
 }
