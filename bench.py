@@ -138,8 +138,9 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--fused", action="store_true", help="single persistent kernel variant instead of the 3-launch default")
-    ap.add_argument("--unfused", action="store_true", help="(default path; kept for old command lines)")
+    ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
+    ap.add_argument("--two-launch", action="store_true", help="summaries+mixing kernel followed by the readout kernel")
+    ap.add_argument("--fused", action="store_true", help="(default path; kept for old command lines)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -159,6 +160,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     normalize = not args.no_normalize
+    path_kw = {"three_launch": True} if args.three_launch else ({"two_launch": True} if args.two_launch else {})
     warm = max(args.warmup, 3)
     M = N // WBLK
 
@@ -169,7 +171,7 @@ def main():
     gathered = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=dev) if (args.gather and world > 1) else None
 
     def step():
-        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, fused=args.fused)
+        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **path_kw)
         if gathered is not None:
             dist.all_gather_into_tensor(gathered, out)
 
@@ -206,7 +208,7 @@ def main():
 
     def e2e_step():
         dq, dk, dv = hq.to(dev, non_blocking=True), hk.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
-        o = mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, fused=args.fused)
+        o = mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, **path_kw)
         hout.copy_(o, non_blocking=True)
 
     e2e_step()

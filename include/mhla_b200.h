@@ -42,9 +42,12 @@ typedef enum mhla_dtype { MHLA_BF16 = 0, MHLA_FP16 = 1 } mhla_dtype;
 
 enum {
   MHLA_FLAG_NORMALIZE = 1 << 0, /* divide by the (quirky) block-mixed normaliser, mhla.py:265-268 */
-  MHLA_FLAG_FUSED = 1 << 7,     /* run the three phases as ONE persistent kernel with in-kernel dependency tracking
-                                 * (lowest DRAM traffic); default: three back-to-back launches chained with PDL */
-  MHLA_FLAG_UNFUSED = 1 << 8,   /* explicit request for the three-launch path (the default) */
+  MHLA_FLAG_FUSED = 1 << 7,     /* explicit request for the default path: ONE persistent kernel, items scheduled at run
+                                 * time, cross-CTA dependencies through per-group counters */
+  MHLA_FLAG_UNFUSED = 1 << 8,   /* three back-to-back launches (summaries, mixing, readout) chained with PDL; used by the
+                                 * tests as an independent cross-check of the fused kernel */
+  MHLA_FLAG_TWO_LAUNCH = 1 << 13, /* summaries + mixing in one dynamically scheduled kernel, then the readout as a second
+                                 * launch that starts on the counters while the first one drains */
   MHLA_FLAG_STOP_AFTER_P1 = 1 << 9,  /* debugging (with UNFUSED): stop after the block summaries */
   MHLA_FLAG_STOP_AFTER_P2 = 1 << 10, /* debugging (with UNFUSED): stop after the block mixing */
   MHLA_FLAG_ONLY_P3 = 1 << 11,       /* debugging (with UNFUSED): run only the readout on a caller-filled workspace */

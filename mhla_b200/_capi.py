@@ -16,6 +16,7 @@ FLAG_STOP_AFTER_P1 = 1 << 9
 FLAG_STOP_AFTER_P2 = 1 << 10
 FLAG_ONLY_P3 = 1 << 11
 FLAG_ONLY_P2 = 1 << 12
+FLAG_TWO_LAUNCH = 1 << 13
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",

@@ -57,6 +57,7 @@ struct alignas(64) BlockmixParams {
   CUtensorMap tmO;                          // out       : rank-5 like q
   uint16_t* ws_S;                           // [G*M][ncols] 16-bit: S_j (Dk*Dv) | n_loc_j hi (wpad) | n_loc_j lo (wpad)
   uint16_t* ws_St;                          // [G*M][Dk*Dv] 16-bit: S~_i
+  const float* wscale;                      // [1]: power of two the mixing matrix was divided by (prep_mix_scaled_kernel)
   const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
   int G, H, M, w, TW, nsub;
@@ -72,6 +73,7 @@ struct alignas(64) BlockmixParams {
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
   int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
+  int o_hint;                               // 1: evict-first L2 hint on the output stores
   int policy;                               // mode 0: 0 = ready P3 items before new P1 items (window), 1 = P3 items last
   int reverse3;                             // mode 3: walk the groups backwards
   int pf_dist;                              // L2 prefetch distance of the producer, in own streaming items (0: off)
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   grid_launch_dependents(); // ... and the next kernel may start its own prologue as soon as SMs free up
   // debug timeline: [mode][cta] = {globaltimer at start of work, at end}, behind the per-CTA counters and the CTA trace
   unsigned long long* const tl = p.prof == nullptr ? nullptr
-      : p.prof + (size_t)gridDim.x * 16 + 4 * 256 * 4 + ((size_t)p.mode * 148 + blockIdx.x) * 2;
+      : p.prof + (size_t)gridDim.x * 16 + 4 * 256 * 4 + ((size_t)p.mode * 148 + blockIdx.x) * 4;
   if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[0] = t; }
 
   ItemStream sched(fifo, q_published);
@@ -351,9 +353,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             if (!wres) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], 32768);
+              const bool need_lo = !p.is_fp16 || tc >= p.n2_scols;
+              mbar_arrive_expect_tx(&full[r.idx()], need_lo ? 32768 : 16384);
               tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
-              tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
+              if (need_lo) tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
               r.advance();
             }
             mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
@@ -512,10 +515,18 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             const uint64_t dhi0 = dsc(tmpl_k, a_addr), dlo0 = dsc(tmpl_k, a_addr + 16384);   // K-major: 32 B per k-step
             const uint64_t db0 = dsc(tmpl_mn8k, ring_addr + r.idx() * kStageBytes);           // MN-major: 2048 B per k-step
             const uint32_t first = slab != 0;
+            // fp16 I/O: the S columns take the "hi" plane only (11 significant bits on a power-of-two normalised matrix -
+            // finer than the 16-bit S it multiplies); the normaliser columns, and everything in bf16 (8-bit planes;
+            // tcgen05 kind::f16 does not take an f16 A with a bf16 B), add the "lo" plane.
+            if (!p.is_fp16 || (it.t % p.n2_cols) >= p.n2_scols) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
-              mma_f16_ss(acc, dlo0 + ks * 2, db0 + ks * 128, idesc_p2, 1u);
+              for (int ks = 0; ks < 4; ++ks) {
+                mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
+                mma_f16_ss(acc, dlo0 + ks * 2, db0 + ks * 128, idesc_p2, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
             }
             if (sa >= 0) mma_commit(&empty[sa]);
             mma_commit(&empty[r.idx()]);
@@ -575,8 +586,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       // CTAs do nothing else, so a P2 item never queues behind streaming items in an in-order pipeline.
       const int np2 = dyn ? p.np2 : 0;
       bool has1 = true, has2 = true, has3 = true;
+      const bool dedicated = np2 > 0 && (int)blockIdx.x < np2;
       if (np2 > 0) {
-        if ((int)blockIdx.x < np2) { has1 = false; has3 = false; } else has2 = false;
+        if (dedicated) has1 = false; else has2 = false;   // (a dedicated CTA joins the readout once the mixing is done)
       }
       if (p.mode == 1) { has2 = false; has3 = false; }
       if (p.mode == 2) { has1 = false; has3 = false; }
@@ -606,19 +618,39 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       long long cur1 = -1, cur2 = -1, cur3 = -1;   // claimed, not yet enqueued
       while (true) {
         {  // claim what is missing; the atomics are independent and overlap
-          const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0;
+          const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0 && !(dedicated && (has2 || cur2 >= 0));
           unsigned long long a1 = 0, a2 = 0, a3 = 0;
           if (n1) a1 = atomicAdd(tickets + 0, 1ull);
           if (n2) a2 = atomicAdd(tickets + 8, 1ull);
           if (n3) a3 = atomicAdd(tickets + 16, 1ull);
-          if (n1) { if ((long long)a1 < n1tot) cur1 = (long long)a1; else has1 = false; }
-          if (n2) { if ((long long)a2 < n2tot) cur2 = (long long)a2; else has2 = false; }
+          if (n1) {
+            if ((long long)a1 < n1tot) cur1 = (long long)a1;
+            else {
+              has1 = false;
+              if (tl != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[2] = t; }
+            }
+          }
+          if (n2) {
+            if ((long long)a2 < n2tot) cur2 = (long long)a2;
+            else {
+              has2 = false;
+              if (tl != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[3] = t; }
+            }
+          }
           if (n3) { if ((long long)a3 < n1tot) cur3 = (long long)a3; else has3 = false; }
         }
-        if (cur1 < 0 && cur2 < 0 && cur3 < 0) break;   // every kind is exhausted
+        if (cur1 < 0 && cur2 < 0 && cur3 < 0 && !(dedicated && has3)) break;   // every kind is exhausted
+        if (cur1 < 0 && cur2 < 0 && cur3 < 0) continue;                         // (dedicated CTA: now claim readout items)
         const int g2 = cur2 >= 0 ? (int)(cur2 / n2per) : -1;
         int g3 = cur3 >= 0 ? (int)(cur3 / p.M) : -1;
         if (g3 >= 0 && rev3) g3 = p.G - 1 - g3;
+        // fused kernel with the readout last: walk the groups backwards (the Q tiles the normaliser pulled in last are
+        // still in L2), except that the final `tail` groups - whose block mixing is still in flight when the readout
+        // begins - come at the very end
+        if (g3 >= 0 && p.mode == 0 && p.policy == 1 && p.reverse3) {
+          const int tail = p.G > 6 ? 3 : 0;
+          if (g3 < p.G - tail) g3 = p.G - tail - 1 - g3;
+        }
         {  // both polls are in flight together: one L2 round trip per decision
           const bool need1 = dep2 && g2 >= 0 && g2 != ready1_g, need2 = dep3 && g3 >= 0 && g3 != ready2_g;
           uint32_t c1 = 0, c2 = 0;
@@ -857,10 +889,11 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
+        const float wsc = __ldg(p.wscale);   // undo the power-of-two normalisation of the mixing matrix (exact)
         if (tc < p.n2_scols) {
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
-            load_pack64(acc + c * 64, 1.0f, pk);
+            load_pack64(acc + c * 64, wsc, pk);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
@@ -872,6 +905,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             if (col0 >= 2 * p.wpad) break;   // uniform: nothing left in this tile
             tmem_ld_x32(acc + q * 32, v);
             tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * wsc);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, v);
             chunk_copy(buf, reinterpret_cast<uint8_t*>(const_cast<float*>(p.den) + row0 * (size_t)(2 * p.wpad) + col0),
@@ -911,7 +946,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_tma_begin();
-            if (et == 0) tma_store_5d(&p.tmO, buf, c * 64, sub * p.TW, i, h, b);
+            // the output is never read again: mark its lines evict-first so that they leave L2 before the Q tiles the
+            // readout of later groups still needs
+            if (et == 0) tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, i, h, b, p.o_hint ? kEvictFirst : kEvictNormal);
             chunk_tma_end();
           }
         }
@@ -991,6 +1028,53 @@ __global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, uin
     }
     out[idx] = hi;
     out[n + idx] = lo;
+  }
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncounters; idx += gridDim.x * blockDim.x)
+    counters[idx] = 0u;
+}
+
+
+// Prologue of the block-mixed path: normalise the fp32 mixing matrix by a power of two (largest magnitude in [0.5, 1)),
+// split it into hi + lo planes [2][M][Mp] of the I/O type (fp16: 22 significant bits together, bf16: 16), publish the power of two for the
+// epilogue and zero the dependency counters / item tickets.  Every block reduces the whole matrix (M*M floats,
+// L2-resident after the first touch) so that no inter-block synchronisation is needed.
+__global__ void prep_mix_scaled_kernel(const float* __restrict__ mix, long long ld, uint16_t* __restrict__ out, int M,
+                                       int Mp, int is_fp16, float* __restrict__ wscale, uint32_t* counters,
+                                       int ncounters) {
+  grid_launch_dependents();
+  // bf16 planes carry the fp32 exponent range: only fp16 needs the normalisation (and pays for the reduction)
+  int e = 0;
+  if (is_fp16) {
+    __shared__ float red[32];
+    float amax = 0.f;
+    const int nn = M * M;
+#pragma unroll 4
+    for (int idx = threadIdx.x; idx < nn; idx += blockDim.x)
+      amax = fmaxf(amax, fabsf(__ldg(mix + (long long)(idx / M) * ld + idx % M)));
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) amax = fmaxf(amax, red[i]);
+    if (amax > 0.f && amax < 3.0e38f) { (void)frexpf(amax, &e); }
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+  }
+  const float down = ldexpf(1.0f, -e);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *wscale = ldexpf(1.0f, e);
+  const int n = M * Mp;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
+    const int i = idx / Mp, j = idx % Mp;
+    float v = 0.f;
+    if (j < M) v = mix[(long long)i * ld + j] * down;
+    if (is_fp16) {
+      const __half h = __float2half_rn(v);
+      out[idx] = __half_as_ushort(h);
+      out[n + idx] = __half_as_ushort(__float2half_rn(v - __half2float(h)));
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out[idx] = __bfloat16_as_ushort(h);
+      out[n + idx] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+    }
   }
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < ncounters; idx += gridDim.x * blockDim.x)
     counters[idx] = 0u;

@@ -203,6 +203,7 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->ws_St = reinterpret_cast<uint16_t*>(St);
   P->den = den;
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
+  P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.G * kCntStride + 48);
   P->G = pl.G; P->H = d->H; P->M = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
   P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
@@ -301,7 +302,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (const char* e = std::getenv("MHLA_RUNAHEAD")) P.run_ahead = std::atoi(e);  // run-time scheduler
   P.np2 = -1;
   P.trace_cta = 0;
-  P.policy = 0;
+  P.policy = 1;
+  P.o_hint = 1;
+  if (const char* e = std::getenv("MHLA_OHINT")) P.o_hint = std::atoi(e);
   if (const char* e = std::getenv("MHLA_POLICY")) P.policy = std::atoi(e);
   P.pf_dist = 0;
   if (const char* e = std::getenv("MHLA_PF")) P.pf_dist = std::atoi(e);
@@ -321,9 +324,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
-  mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mix, (long long)d->mix_ld,
-                                               reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp, 0, 1.0f,
-                                               d->dtype == MHLA_FP16, P.counters, 2 * pl.G * kCntStride + 64);
+  mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
+                                                     reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp, d->dtype == MHLA_FP16,
+                                                     const_cast<float*>(P.wscale), P.counters, 2 * pl.G * kCntStride + 48);
   ++launches;
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
   auto launch_pdl = [&](int grid) -> bool {
@@ -339,15 +342,16 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     cfg.numAttrs = 1;
     return cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx");
   };
-  if (!(d->flags & MHLA_FLAG_FUSED)) {
+  const bool dbg_phase = (d->flags & (MHLA_FLAG_STOP_AFTER_P1 | MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2)) != 0;
+  const bool single = (d->flags & MHLA_FLAG_FUSED) || !(dbg_phase || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
+  if (!single) {
     int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
     int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
     if (d->flags & MHLA_FLAG_ONLY_P2) first = last = 2;
-    // Default: two launches chained with PDL - summaries + block mixing in one dynamically scheduled kernel (mode 4:
-    // the mixing of a group starts as soon as its summaries are complete and overlaps the streaming of later groups),
-    // then the readout with the groups walked backwards (the Q tiles the normaliser read last are still in L2).
-    // MHLA_FLAG_UNFUSED and the debugging flags select the plain phase-by-phase launches instead.
-    const bool two_launch = first == 1 && last == 3 && !(d->flags & MHLA_FLAG_UNFUSED) && !std::getenv("MHLA_THREE_LAUNCH");
+    // MHLA_FLAG_TWO_LAUNCH: summaries + block mixing in one dynamically scheduled kernel (mode 4: the mixing of a group
+    // starts as soon as its summaries are complete), then the readout as a second launch that starts on the counters
+    // while the first grid drains (mode 5).  MHLA_FLAG_UNFUSED / the debugging flags: plain phase-by-phase launches.
+    const bool two_launch = first == 1 && last == 3 && (d->flags & MHLA_FLAG_TWO_LAUNCH) != 0;
     P.reverse3 = two_launch ? 1 : 0;
     if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     for (int mode = first; mode <= last; ++mode) {
@@ -368,6 +372,8 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     }
   } else {
     P.mode = 0;
+    P.reverse3 = 0;
+    if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     P.slot_bytes = 16384;
     P.ring_stages = 5;
     const long long items = (long long)pl.G * (n1 + n2 + n3);

@@ -166,6 +166,13 @@ __device__ __forceinline__ void tma_store_5d(const void* tmap, const void* smem,
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+__device__ __forceinline__ void tma_store_5d_hint(const void* tmap, const void* smem, int c0, int c1, int c2, int c3,
+                                                  int c4, uint64_t hint) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(hint)
+               : "memory");
+}
 // 1-D bulk copy shared -> global (no tensor map); size multiple of 16, both addresses 16-byte aligned
 __device__ __forceinline__ void bulk_store_1d(void* gdst, const void* smem, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(gdst)),
@@ -259,6 +266,13 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
 __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_major, uint32_t b_major, uint32_t M,
                                                   uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
+}
+
+// same with different A / B element formats (kind::f16 takes f16 and bf16 operands in any combination)
+__host__ __device__ constexpr uint32_t make_idesc2(uint32_t afmt, uint32_t bfmt, uint32_t a_major, uint32_t b_major,
+                                                   uint32_t M, uint32_t N) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_major << 15) | (b_major << 16) | ((N >> 3) << 17) |
          ((M >> 4) << 24);
 }
 

@@ -63,8 +63,8 @@ def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
 
 
 def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
-                  out: Optional[torch.Tensor] = None, fused: bool = False, unfused: Optional[bool] = None,
-                  three_launch: bool = False, debug_flags: int = 0) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, fused: bool = True, unfused: Optional[bool] = None,
+                  three_launch: bool = False, two_launch: bool = False, debug_flags: int = 0) -> torch.Tensor:
     """Non-causal block-mixed MHLA forward on block-major tensors.
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
@@ -72,8 +72,9 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
               stride is a multiple of 8 elements.
     mix     : [M, M] (or the Conv2d weight [M, M, 1, 1]); out_i = sum_j mix[i, j] (.)_j.
     q_rope, k_rope : roped copies for the numerator (variant B); q, k then only feed the normaliser.
-    fused   : run the three phases as one persistent kernel with in-kernel dependency tracking (lowest DRAM traffic)
-              instead of the default three PDL-chained launches of the same kernel.
+    fused   : (default) one persistent kernel: items are scheduled at run time, cross-CTA dependencies go through
+              per-group counters.  ``three_launch`` / ``unfused=True`` run the phases as three PDL-chained launches of
+              the same kernel (an independent cross-check), ``two_launch`` as summaries+mixing followed by the readout.
     """
     _require_cuda(q, k, v, mix, q_rope, k_rope)
     if (q_rope is None) != (k_rope is None):
@@ -101,10 +102,12 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     d = _capi.BlockmixDesc()
     d.B, d.H, d.M, d.w, d.D = B, H, M, w, D
     d.dtype = _DT[cdtype]
-    if unfused is not None:          # legacy spelling used by the tests: unfused=False -> the single fused kernel
-        fused = not unfused
-    d.flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_FUSED if fused else 0) |
-               (_capi.FLAG_UNFUSED if three_launch else 0) | int(debug_flags))
+    if unfused is not None:          # spelling used by the tests: unfused=True -> three launches
+        three_launch = bool(unfused)
+    d.flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else 0) |
+               (_capi.FLAG_TWO_LAUNCH if two_launch else 0) | int(debug_flags))
+    if not fused and not (three_launch or two_launch or debug_flags):
+        d.flags |= _capi.FLAG_TWO_LAUNCH
     d.eps = float(eps)
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)

@@ -55,12 +55,14 @@ def _run(q, k, v, W, qr=None, kr=None, normalize=True, eps=1e-6, **kw):
     (1, 2, 5, 100, 64, True, False, torch.float16),         # ragged w, fp16
     (1, 1, 1, 256, 64, True, False, torch.bfloat16),        # single block
 ])
-@pytest.mark.parametrize("unfused", [False, True])
-def test_blockmix_vs_oracle(B, H, M, w, D, normalize, rope, dtype, unfused):
+@pytest.mark.parametrize("path", ["fused", "three_launch", "two_launch"])
+def test_blockmix_vs_oracle(B, H, M, w, D, normalize, rope, dtype, path):
+    """Every launch structure of the C ABI (the default single fused kernel, the three PDL-chained phase launches and
+    the two-launch variant) against the oracle."""
     q, k, v, qr, kr = _inputs(B, H, M, w, D, dtype, rope=rope)
     g = torch.Generator().manual_seed(1)
     W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
-    out = _run(q, k, v, W, qr, kr, normalize=normalize, unfused=unfused)
+    out = _run(q, k, v, W, qr, kr, normalize=normalize, **({} if path == "fused" else {path: True}))
     ref = oracle.blockmix_fwd(q, k, v, W, normalize=normalize, q_rope=qr, k_rope=kr)
     _check(ref, out, dtype)
 

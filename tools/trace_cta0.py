@@ -14,13 +14,13 @@ normalize = "--no-normalize" not in sys.argv
 tag = "norm" if normalize else "nonorm"
 kw = dict(fused=True)
 if "--p1only" in sys.argv:
-    kw = dict(unfused=True, debug_flags=_capi.FLAG_STOP_AFTER_P1)
+    kw = dict(debug_flags=_capi.FLAG_STOP_AFTER_P1)
     tag += "_p1only"
 if "--p2only" in sys.argv:
-    kw = dict(unfused=True, debug_flags=_capi.FLAG_ONLY_P2)
+    kw = dict(debug_flags=_capi.FLAG_ONLY_P2)
     tag += "_p2only"
 if "--p3only" in sys.argv:
-    kw = dict(unfused=True, debug_flags=_capi.FLAG_ONLY_P3)
+    kw = dict(debug_flags=_capi.FLAG_ONLY_P3)
     tag += "_p3only"
 B, H, M, w, D = 2, 16, 128, 256, 64
 dev = torch.device("cuda")
