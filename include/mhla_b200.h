@@ -48,6 +48,11 @@ enum {
                                  * tests as an independent cross-check of the fused kernel */
   MHLA_FLAG_TWO_LAUNCH = 1 << 13, /* summaries + mixing in one dynamically scheduled kernel, then the readout as a second
                                  * launch that starts on the counters while the first one drains */
+  MHLA_FLAG_WS_PERSISTENT = 1 << 14, /* the workspace is owned by this library's caller exclusively for this descriptor
+                                 * shape: it was zeroed once (mhla_blockmix_workspace_init) and has only been used by
+                                 * calls carrying this flag since.  The fused kernel then needs no prologue launch (its
+                                 * CTAs split the mixing matrix themselves and the last one to finish re-zeroes the
+                                 * control block): ONE launch per call.  Ignored by the multi-launch paths. */
   MHLA_FLAG_STOP_AFTER_P1 = 1 << 9,  /* debugging (with UNFUSED): stop after the block summaries */
   MHLA_FLAG_STOP_AFTER_P2 = 1 << 10, /* debugging (with UNFUSED): stop after the block mixing */
   MHLA_FLAG_ONLY_P3 = 1 << 11,       /* debugging (with UNFUSED): run only the readout on a caller-filled workspace */
@@ -95,6 +100,8 @@ size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);
  * then ncols (floats per S row: D*D summaries followed by wpad n_loc entries), wpad, padded mix pitch. */
 int mhla_blockmix_workspace_layout(const mhla_blockmix_desc* desc, size_t out[8]);
 int mhla_fwd_blockmix(const mhla_blockmix_desc* desc, void* stream);
+/* Zero the control block of a workspace (enqueued on `stream`) before its first use with MHLA_FLAG_WS_PERSISTENT. */
+int mhla_blockmix_workspace_init(const mhla_blockmix_desc* desc, void* stream);
 
 /*
  * Causal chunked forward (variant C), replaces naive_chunk_simple_mhla_fixed

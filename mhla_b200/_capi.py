@@ -17,10 +17,11 @@ FLAG_STOP_AFTER_P2 = 1 << 10
 FLAG_ONLY_P3 = 1 << 11
 FLAG_ONLY_P2 = 1 << 12
 FLAG_TWO_LAUNCH = 1 << 13
+FLAG_WS_PERSISTENT = 1 << 14
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
-    "mhla_blockmix_workspace_bytes", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
 ]
 
 
@@ -79,6 +80,8 @@ def lib() -> C.CDLL:
         L.mhla_blockmix_workspace_layout.argtypes = [C.POINTER(BlockmixDesc), C.POINTER(C.c_size_t * 8)]
         L.mhla_fwd_blockmix.restype = C.c_int
         L.mhla_fwd_blockmix.argtypes = [C.POINTER(BlockmixDesc), C.c_void_p]
+        L.mhla_blockmix_workspace_init.restype = C.c_int
+        L.mhla_blockmix_workspace_init.argtypes = [C.POINTER(BlockmixDesc), C.c_void_p]
         L.mhla_causal_workspace_bytes.restype = C.c_size_t
         L.mhla_causal_workspace_bytes.argtypes = [C.POINTER(CausalDesc)]
         L.mhla_fwd_causal.restype = C.c_int

@@ -57,6 +57,11 @@ struct alignas(64) BlockmixParams {
   CUtensorMap tmO;                          // out       : rank-5 like q
   uint16_t* ws_S;                           // [G*M][ncols] 16-bit: S_j (Dk*Dv) | n_loc_j hi (wpad) | n_loc_j lo (wpad)
   uint16_t* ws_St;                          // [G*M][Dk*Dv] 16-bit: S~_i
+  const float* mix;                         // self_prep: the caller's fp32 mixing matrix [M][mix_ld]
+  long long mix_ld;
+  uint16_t* w_planes;                       // [2][M][Mp] hi | lo planes of the mixing matrix (I/O type)
+  int Mp, self_prep;                        // self_prep: no prologue kernel - the CTAs split the matrix and the last one to
+                                            // finish re-zeroes the control block (persistent, library-owned workspace)
   const float* wscale;                      // [1]: power of two the mixing matrix was divided by (prep_mix_scaled_kernel)
   const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
@@ -196,6 +201,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint32_t* q_published = tmem_slot + 1;   // items the scheduler warp (warp 2) has enqueued
   uint32_t* q_started = tmem_slot + 2;     // items the producer has picked up (throttles the scheduler's run-ahead)
   uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished by each epilogue warpgroup
+  float* wscale_s = reinterpret_cast<float*>(tmem_slot + 5);   // self_prep: power of two the mixing matrix was divided by
+  uint32_t* last_flag = tmem_slot + 6;     // self_prep: this CTA is the last one to finish
   uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + kSmemFifo);
 
   const int warp = threadIdx.x >> 5;
@@ -275,6 +282,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           }
       };
       if (wres) {
+        if (p.self_prep) {   // the planes are being written by the CTAs of this very launch: wait until all have announced
+          spin_until(p.counters + (size_t)2 * p.G * p.cnt_stride + 64, gridDim.x);
+          fence_proxy_async_all();
+        }
         for (int slab = 0; slab < p.kslabs; ++slab) {
           uint8_t* st = ring + slab * kStageBytes;
           mbar_arrive_expect_tx(&full[slab], 32768);
@@ -602,6 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint32_t run_ahead = (uint32_t)p.run_ahead;
       uint32_t pub = 0;
       int ready1_g = -1, ready2_g = -1;   // groups already known to have all P1 / all P2 items done
+      bool w_ok = !p.self_prep;           // the planes of the mixing matrix are complete (self_prep: every CTA has announced)
       auto emit = [&](int type, int g, int t) {
         uint32_t spins = 0;
         while (pub - ld_acquire_cta_shared(q_started) >= run_ahead) {
@@ -657,9 +669,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (need1) c1 = ld_acquire_gpu(p.counters + (size_t)g2 * p.cnt_stride);
           if (need2) c2 = ld_acquire_gpu(p.counters + (size_t)(p.G + g3) * p.cnt_stride);
           if (need1 && c1 >= (uint32_t)p.M) ready1_g = g2;
+          if (!w_ok && g2 >= 0) w_ok = ld_acquire_gpu(p.counters + (size_t)2 * p.G * p.cnt_stride + 64) >= gridDim.x;
           if (need2 && c2 >= (uint32_t)n2per) ready2_g = g3;
         }
-        const bool can2 = g2 >= 0 && (!dep2 || ready1_g == g2);
+        const bool can2 = g2 >= 0 && (!dep2 || ready1_g == g2) && w_ok;
         const bool can3 = g3 >= 0 && (!dep3 || ready2_g == g3);
         const bool can1 = cur1 >= 0 && (p.mode != 0 || p.policy == 1 || g3 < 0 || (int)(cur1 / p.M) < g3 + p.window);
         // Items alternate between the two epilogue warpgroups (FIFO index parity) and a P1 epilogue (normaliser) costs
@@ -811,6 +824,43 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       return acc_n;
     };
 
+    if (p.self_prep) {
+      // No prologue kernel: the 256 epilogue threads of every CTA split their share of the fp32 mixing matrix into the
+      // hi | lo planes the P2 items load by TMA (rows blockIdx.x, blockIdx.x + gridDim.x, ...) and announce it; the
+      // scheduler holds P2 items back until every CTA has done so.  The first summaries are still in flight meanwhile.
+      const int t256 = (int)threadIdx.x - 128;
+      float down = 1.0f;
+      if (p.is_fp16) {   // fp16 planes: normalise by a power of two (every CTA reduces the whole matrix - it is tiny)
+        float amax = 0.f;
+        const int nn = p.M * p.M;
+        for (int idx = t256; idx < nn; idx += 256) amax = fmaxf(amax, fabsf(__ldg(p.mix + (long long)(idx / p.M) * p.mix_ld + idx % p.M)));
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        float* red = reinterpret_cast<float*>(smem + kSmemKsum);   // scratch: the ksum area is not in use yet
+        if (lane == 0) red[warp - 4] = amax;
+        named_bar_sync(9, 256);
+        amax = 0.f;
+        for (int i = 0; i < 8; ++i) amax = fmaxf(amax, red[i]);
+        named_bar_sync(9, 256);
+        int e = 0;
+        if (amax > 0.f && amax < 3.0e38f) { (void)frexpf(amax, &e); }
+        e = e < -100 ? -100 : (e > 100 ? 100 : e);
+        down = ldexpf(1.0f, -e);
+        if (t256 == 0) *wscale_s = ldexpf(1.0f, e);
+      } else if (t256 == 0) {
+        *wscale_s = 1.0f;
+      }
+      const int nplane = p.M * p.Mp;
+      for (int row = blockIdx.x; row < p.M; row += gridDim.x)
+        for (int j = t256; j < p.Mp; j += 256) {
+          const float val = j < p.M ? __ldg(p.mix + (long long)row * p.mix_ld + j) * down : 0.f;
+          uint16_t hi, lo;
+          split16(val, hi, lo);
+          p.w_planes[row * p.Mp + j] = hi;
+          p.w_planes[nplane + row * p.Mp + j] = lo;
+        }
+      named_bar_sync(9, 256);
+      if (t256 == 0) red_release_gpu_add(p.counters + (size_t)2 * p.G * p.cnt_stride + 64, 1u);
+    }
     while (sched.next_warp(it, lane)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
@@ -889,7 +939,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
-        const float wsc = __ldg(p.wscale);   // undo the power-of-two normalisation of the mixing matrix (exact)
+        const float wsc = p.self_prep ? *wscale_s : __ldg(p.wscale);   // undo the power-of-two normalisation (exact)
         if (tc < p.n2_scols) {
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
@@ -1006,6 +1056,21 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   __syncthreads();
   if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[1] = t; }
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  if (p.self_prep) {
+    // The last CTA to get here re-zeroes the control block (counters, tickets, flags) for the next call: every other
+    // CTA has made its last access to it before incrementing the exit counter.
+    uint32_t* const tail = p.counters + (size_t)2 * p.G * p.cnt_stride;
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *last_flag = (atomicAdd(tail + 80, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*last_flag) {
+      __threadfence();
+      const int nwords = 2 * p.G * p.cnt_stride + 128;
+      for (int idx = threadIdx.x; idx < nwords; idx += blockDim.x) p.counters[idx] = 0u;
+    }
+  }
 }
 
 // Tiny prologue: split the fp32 mixing matrix into hi + lo 16-bit planes [2][M][Mp] (optionally keeping only the

@@ -109,7 +109,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->off_St = off;  off = align_up(off + GM * D * D * 2, 1024);
   pl->off_den = off; off = align_up(off + GM * (pl->wpad ? 2 * pl->wpad : 32) * 4, 1024);
   pl->off_W = off;   off = align_up(off + (size_t)2 * d->M * pl->Mp * 2, 1024);
-  pl->off_cnt = off; off = align_up(off + ((size_t)2 * pl->G * kCntStride + 64) * 4, 1024);   // + 3 item tickets
+  pl->off_cnt = off; off = align_up(off + ((size_t)2 * pl->G * kCntStride + 128) * 4, 1024);   // + item tickets, flags
   pl->total = off;
   return MHLA_OK;
 }
@@ -204,6 +204,7 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->den = den;
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
   P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.G * kCntStride + 48);
+  P->mix = d->mix; P->mix_ld = d->mix_ld; P->w_planes = Wp; P->Mp = pl.Mp; P->self_prep = 0;
   P->G = pl.G; P->H = d->H; P->M = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
   P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
@@ -324,10 +325,17 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
-  mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
-                                                     reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp, d->dtype == MHLA_FP16,
-                                                     const_cast<float*>(P.wscale), P.counters, 2 * pl.G * kCntStride + 48);
-  ++launches;
+  const bool dbg_phase = (d->flags & (MHLA_FLAG_STOP_AFTER_P1 | MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2)) != 0;
+  const bool single = (d->flags & MHLA_FLAG_FUSED) || !(dbg_phase || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
+  P.self_prep = (single && (d->flags & MHLA_FLAG_WS_PERSISTENT) && !std::getenv("MHLA_NO_SELF_PREP")) ? 1 : 0;
+  if (!P.self_prep) {
+    mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
+                                                       reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp,
+                                                       d->dtype == MHLA_FP16, const_cast<float*>(P.wscale), P.counters,
+                                                       2 * pl.G * kCntStride + 48);
+    // (words 48.. of the tail: wscale and the self_prep flags - the prologue kernel leaves them alone)
+    ++launches;
+  }
   const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
   auto launch_pdl = [&](int grid) -> bool {
     cudaLaunchConfig_t cfg{};
@@ -342,8 +350,6 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     cfg.numAttrs = 1;
     return cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx");
   };
-  const bool dbg_phase = (d->flags & (MHLA_FLAG_STOP_AFTER_P1 | MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2)) != 0;
-  const bool single = (d->flags & MHLA_FLAG_FUSED) || !(dbg_phase || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
   if (!single) {
     int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
     int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
@@ -379,7 +385,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     const long long items = (long long)pl.G * (n1 + n2 + n3);
     const int grid = (int)(items < g_num_sms ? items : g_num_sms);
     // dedicated block-mixing CTAs: one per P2 tile of a group, when that leaves most of the grid for streaming
-    if (P.np2 < 0) P.np2 = (n2 * 4 <= grid) ? (int)n2 : 0;
+    if (P.np2 < 0) P.np2 = 0;   // (dedicated mixing CTAs are a tuning option: MHLA_NP2)
     if (P.np2 > grid / 2) P.np2 = grid / 2;
     if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
     ++launches;
@@ -392,6 +398,18 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 /* Debug hook (not part of the stable ABI): device buffer of [#SMs][16] uint64 that receives per-CTA wait-cycle counters
  * of the blockmix kernel's warp roles; NULL switches the instrumentation off. */
 void mhla_debug_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
+
+int mhla_blockmix_workspace_init(const mhla_blockmix_desc* d, void* stream_) {
+  BlockmixPlan pl;
+  int rc = plan_blockmix(d, &pl);
+  if (rc != MHLA_OK) return rc;
+  if (!d->workspace || d->workspace_bytes < pl.total) return MHLA_ERR_WORKSPACE;
+  uint8_t* ws = static_cast<uint8_t*>(d->workspace);
+  if (!cuda_ok(cudaMemsetAsync(ws + pl.off_cnt, 0, pl.total - pl.off_cnt, static_cast<cudaStream_t>(stream_)),
+               "cudaMemsetAsync"))
+    return MHLA_ERR_CUDA;
+  return MHLA_OK;
+}
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }
 

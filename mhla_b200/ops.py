@@ -55,6 +55,23 @@ def _prep(t: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tenso
     return t
 
 
+# Persistent workspaces of the fused path, one per (device, stream, size): zeroed once, then self-cleaning (the kernel's
+# last CTA re-zeroes the control block), so a call is a single kernel launch.  A handful of shapes are kept alive.
+_WS_CACHE: "dict[tuple, torch.Tensor]" = {}
+_WS_CACHE_MAX = 4
+
+
+def _persistent_ws(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, nbytes)
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        if len(_WS_CACHE) >= _WS_CACHE_MAX:
+            _WS_CACHE.pop(next(iter(_WS_CACHE)))
+        ws = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=device)
+        _WS_CACHE[key] = ws
+    return ws
+
+
 def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
     if t is None:
         return _capi.Tensor5(None, 0, 0, 0, 0)
@@ -116,7 +133,12 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     nbytes = L.mhla_blockmix_workspace_bytes(C.byref(d))
     if nbytes == 0:
         raise _capi.MhlaError(f"unsupported blockmix shape B={B} H={H} M={M} w={w} D={D} (need D in {{64,128}}, w<=256)")
-    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    single = not (three_launch or two_launch or debug_flags or not fused)
+    if single:
+        ws = _persistent_ws(q.device, nbytes)
+        d.flags |= _capi.FLAG_WS_PERSISTENT
+    else:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
     base = (ws.data_ptr() + 1023) // 1024 * 1024
     d.workspace, d.workspace_bytes = base, nbytes
     with torch.cuda.device(q.device):
