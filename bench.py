@@ -6,7 +6,8 @@
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # N>1: one rank per GPU, (b,h)-units sharded
 
 A "step" is one pass of the operator over one batch of synthetic block-major [B, H, M, w, D] tensors
-(w = 256, M = N / 256, W = BlockDistanceConv3D((M,1,1), "linear")), normaliser ON (DiT semantics).  Multi-GPU is
+(w = 256, M = N / 256, W = BlockDistanceConv3D((M,1,1), "linear")), normaliser ON (DiT semantics): ONE launch of the fused
+persistent kernel per step (`--three-launch` / `--two-launch` time the multi-launch variants of the same kernel).  Multi-GPU is
 weak scaling over independent (b,h) units: every rank processes a full B=2,H=16 batch (global batch 2N), no
 data-path collective (`--gather` adds one NCCL all-gather of the outputs for the consumers that need all heads).
 """
@@ -34,6 +35,16 @@ def measured_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def measured_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dram_bytes_per_launch"])
+    except Exception:
+        return None
 
 
 def make_inputs(device, seed, b=B, h=H, n=N, d=D, w=WBLK, pin=False):
@@ -246,9 +257,10 @@ def main():
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src,
+            "traffic": (measured_traffic() if (normalize and not path_kw) else None), "peak_source": peak_src,
             "note": "algorithmic bytes = Q,K,V read + O write = 4*B*H*N*D*2 = 536.9 MB per launch; duration = CUDA-event "
-                    "time per step (includes the ~2 us mixing-matrix prologue kernel)",
+                    "time per step = one launch of blockmix_kernel<64> (the only kernel of a step); traffic = dram read + "
+                    "write bytes of that launch from the committed ncu --set full capture (profiles/r01_traffic.json)",
         },
         "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
                 "ms_per_step": ms_e2e / args.e2e_steps},
