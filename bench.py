@@ -218,9 +218,13 @@ def main():
     hout = torch.empty(out.shape, dtype=out.dtype).pin_memory()
 
     def e2e_step():
-        dq, dk, dv = hq.to(dev, non_blocking=True), hk.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
-        o = mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, **path_kw)
-        hout.copy_(o, non_blocking=True)
+        # the public host-tensor entry point: pinned H2D of q,k,v, the kernel and the D2H of the output, pipelined over
+        # ranges of (b,h) units on three streams (mhla_b200.ops.mhla_host)
+        if path_kw:
+            dq, dk, dv = hq.to(dev, non_blocking=True), hk.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
+            hout.copy_(mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, **path_kw), non_blocking=True)
+        else:
+            mhla_b200.mhla_host(hq, hk, hv, W, out=hout, normalize=normalize)
 
     e2e_step()
     torch.cuda.synchronize()

@@ -76,6 +76,8 @@ struct alignas(64) BlockmixParams {
   int np2;                                  // fused mode: CTAs [0, np2) run only P2 items (0: every CTA owns P2 items too)
   float eps;
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
+  int mix_hi_only;                          // bf16: S columns of the block mixing take the 8-bit hi plane only (MHLA_FLAG_FAST_MIX)
+  int slots_per_wg;                         // staging slots per epilogue warpgroup (2, or 1 to buy another ring stage)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
   int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
   int o_hint;                               // 1: evict-first L2 hint on the output stores
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             if (!wres) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               st = ring + r.idx() * kStageBytes;
-              const bool need_lo = !p.is_fp16 || tc >= p.n2_scols;
+              const bool need_lo = !(p.is_fp16 || p.mix_hi_only) || tc >= p.n2_scols;
               mbar_arrive_expect_tx(&full[r.idx()], need_lo ? 32768 : 16384);
               tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
               if (need_lo) tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             // fp16 I/O: the S columns take the "hi" plane only (11 significant bits on a power-of-two normalised matrix -
             // finer than the 16-bit S it multiplies); the normaliser columns, and everything in bf16 (8-bit planes;
             // tcgen05 kind::f16 does not take an f16 A with a bf16 B), add the "lo" plane.
-            if (!p.is_fp16 || (it.t % p.n2_cols) >= p.n2_scols) {
+            if (!(p.is_fp16 || p.mix_hi_only) || (it.t % p.n2_cols) >= p.n2_scols) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
@@ -709,7 +711,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     ksum_s += wg * 128;
     const uint32_t bar_base = 1 + wg * 4;    // named barrier ids of this warpgroup
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
-    uint8_t* const my_staging = staging + wg * 2 * slot_bytes;
+    const int nslots = p.slots_per_wg;
+    uint8_t* const my_staging = staging + wg * nslots * slot_bytes;
     Ring r(nst, wres ? p.kslabs : 0);
     uint32_t nitem = 0;
     uint32_t nchunk = 0;                     // staging chunks written so far (slot = nchunk & 1)
@@ -730,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     };
     // next staging slot; a TMA store that is still reading it (issued two chunks ago) must have finished
     auto slot_acquire = [&]() -> uint8_t* {
-      const int s_ = (int)(nchunk & 1);
+      const int s_ = nslots == 1 ? 0 : (int)(nchunk & 1);
       const long long t0 = prof_on ? clock64() : 0;
       if (et == 0 && last_tma_slot >= 0) {
         if (last_tma_slot == s_) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
@@ -763,7 +766,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // rows of the slot are complete: thread 0 sends it with TMA
     auto chunk_tma_begin = [&]() { fence_proxy_async_smem(); named_bar_sync(bar_base, kEpiThreads); };
     auto chunk_tma_end = [&]() {
-      if (et == 0) { tma_store_commit(); last_tma_slot = (int)(nchunk & 1); }
+      if (et == 0) { tma_store_commit(); last_tma_slot = nslots == 1 ? 0 : (int)(nchunk & 1); }
       ++nchunk;
     };
     // every global store of this item has been issued by all 128 threads: publish

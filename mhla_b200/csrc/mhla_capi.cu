@@ -303,6 +303,8 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (const char* e = std::getenv("MHLA_RUNAHEAD")) P.run_ahead = std::atoi(e);  // run-time scheduler
   P.np2 = -1;
   P.trace_cta = 0;
+  P.mix_hi_only = 0;
+  if (const char* e = std::getenv("MHLA_MIX_HI_ONLY")) P.mix_hi_only = std::atoi(e);
   P.policy = 1;
   P.o_hint = 1;
   if (const char* e = std::getenv("MHLA_OHINT")) P.o_hint = std::atoi(e);
@@ -368,6 +370,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
       const bool small_staging = (P.mode == 1 && d->D == 64);
       P.slot_bytes = small_staging ? 8192 : 16384;
       P.ring_stages = small_staging ? 6 : 5;
+      P.slots_per_wg = 2;
       if (P.mode == 4 && P.np2 < 0) P.np2 = 0;
       const long long items = (long long)pl.G * (P.mode == 4 ? n1 + n2 : (mode == 1 ? n1 : (mode == 2 ? n2 : n3)));
       if (P.mode != 4 && P.mode != 0) P.np2 = 0;
@@ -381,7 +384,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     P.reverse3 = 0;
     if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     P.slot_bytes = 16384;
-    P.ring_stages = 5;
+    P.slots_per_wg = 2;
+    if (const char* e = std::getenv("MHLA_SLOTS")) P.slots_per_wg = std::atoi(e) == 1 ? 1 : 2;
+    P.ring_stages = P.slots_per_wg == 1 ? 6 : 5;   // one staging slot per warpgroup buys a sixth ring stage
     const long long items = (long long)pl.G * (n1 + n2 + n3);
     const int grid = (int)(items < g_num_sms ? items : g_num_sms);
     // dedicated block-mixing CTAs: one per P2 tile of a group, when that leaves most of the grid for streaming

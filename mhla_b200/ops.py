@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -154,6 +154,60 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         if in_dtype != cdtype:
             res = res.to(in_dtype)
     return res
+
+
+_HOST_STREAMS: "dict[int, tuple]" = {}
+
+
+def mhla_host(q, k, v, mix, *, out: Optional[torch.Tensor] = None, device=None, eps: float = 1e-6, normalize: bool = True,
+              chunks: int = 4) -> torch.Tensor:
+    """Block-mixed forward for HOST tensors ([B, H, M, w, D], ideally pinned): the (b,h) units are independent, so the
+    batch is cut into `chunks` contiguous ranges of units and the host->device copies of range c+1, the kernel of range
+    c and the device->host copy of range c-1 run concurrently on three streams (PCIe is full duplex; the kernel time
+    disappears behind the copies).  Returns a host tensor (`out`, pinned if given so, else freshly pinned)."""
+    if q.is_cuda:
+        raise ValueError("mhla_host takes host tensors; use mhla() for device tensors")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    B, H, M, w, D = q.shape
+    if out is None:
+        out = torch.empty(q.shape, dtype=q.dtype).pin_memory()
+    units = B * H
+    chunks = max(1, min(chunks, units))
+    qf, kf, vf, of = (t.reshape(units, 1, M, w, D) for t in (q, k, v, out))   # a unit is a (b,h) pair: [units, 1, M, w, D]
+    with torch.cuda.device(dev):
+        if dev.index not in _HOST_STREAMS:
+            _HOST_STREAMS[dev.index] = (torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream())
+        s_in, s_run, s_out = _HOST_STREAMS[dev.index]
+        cur = torch.cuda.current_stream()
+        for s_ in (s_in, s_run, s_out):
+            s_.wait_stream(cur)
+        mix_d = mix.to(dev, non_blocking=True) if not mix.is_cuda else mix
+        s_run.wait_stream(cur)
+        dq = torch.empty((units, 1, M, w, D), dtype=q.dtype, device=dev)
+        dk, dv, do = torch.empty_like(dq), torch.empty_like(dq), torch.empty_like(dq)
+        per = (units + chunks - 1) // chunks
+        for c in range(chunks):
+            lo, hi = c * per, min(units, (c + 1) * per)
+            if lo >= hi:
+                break
+            with torch.cuda.stream(s_in):
+                dq[lo:hi].copy_(qf[lo:hi], non_blocking=True)
+                dk[lo:hi].copy_(kf[lo:hi], non_blocking=True)
+                dv[lo:hi].copy_(vf[lo:hi], non_blocking=True)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_in)
+                mhla_blockmix(dq[lo:hi], dk[lo:hi], dv[lo:hi], mix_d, eps=eps, normalize=normalize, out=do[lo:hi])
+                ev_run = torch.cuda.Event()
+                ev_run.record(s_run)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_run)
+                of[lo:hi].copy_(do[lo:hi], non_blocking=True)
+        cur.wait_stream(s_out)
+        for t in (dq, dk, dv, do):
+            t.record_stream(s_in); t.record_stream(s_run); t.record_stream(s_out)
+    return out
 
 
 def _t4(t: torch.Tensor) -> _capi.Tensor4:

@@ -144,6 +144,20 @@ def test_blockmix_permutation_catches_fixed_normaliser():
     assert oracle.err_ratio(r1[:, :, 0], r2[:, :, 0]) > 1e-3      # block 0's outputs change although its tokens did not
 
 
+def test_host_pipeline_matches_device_call():
+    """mhla_host (pinned host tensors, copies and kernels pipelined over ranges of (b,h) units) is bit-identical to one
+    device call on the whole batch - the units are independent."""
+    import mhla_b200
+    B, H, M, w, D = 2, 6, 16, 64, 64
+    q, k, v, _, _ = _inputs(B, H, M, w, D, torch.bfloat16, seed=11)
+    W = oracle.block_distance_matrix((4, 4), "linear")
+    ref = _run(q, k, v, W)
+    for chunks in (1, 4, 5):
+        out = mhla_b200.mhla_host(q.pin_memory(), k.pin_memory(), v.pin_memory(), W.cuda(), chunks=chunks)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref.cpu())
+
+
 def test_errors_are_loud():
     import mhla_b200
     q = torch.zeros(1, 1, 2, 16, 32, dtype=torch.bfloat16, device="cuda")
