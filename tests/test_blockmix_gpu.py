@@ -144,6 +144,30 @@ def test_blockmix_permutation_catches_fixed_normaliser():
     assert oracle.err_ratio(r1[:, :, 0], r2[:, :, 0]) > 1e-3      # block 0's outputs change although its tokens did not
 
 
+@pytest.mark.parametrize("name,B,H,M,w,D,normalize,rope", [
+    ("cfg2 DiT-S/2 256x256, batch 64", 64, 6, 16, 16, 64, True, False),          # BASELINE cfg2 at a realistic batch
+    ("cfg4 Wan2.1-1.3B 81x480x800, shipped (no normaliser)", 1, 12, 150, 210, 128, False, True),
+    ("cfg4 Wan2.1-1.3B, normaliser on, CFG batch 2", 2, 12, 150, 210, 128, True, True),
+])
+def test_blockmix_full_size_configs(name, B, H, M, w, D, normalize, rope):
+    """BASELINE configs at their full sizes: the whole batch runs on the GPU, a few (b,h) units are checked against the
+    oracle (the oracle is per-unit independent, so the rest is covered by the bitwise shard-equivalence test)."""
+    import mhla_b200
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mk = lambda relu: (torch.relu(torch.randn(B, H, M, w, D, generator=g, device="cuda")) + 1e-6 if relu  # noqa: E731
+                       else torch.randn(B, H, M, w, D, generator=g, device="cuda")).bfloat16()
+    q, k, v = mk(True), mk(True), mk(False)
+    qr, kr = (mk(False), mk(False)) if rope else (None, None)
+    W = torch.rand(M, M, generator=torch.Generator().manual_seed(4)) / M + 0.5 * torch.eye(M) / M
+    out = mhla_b200.mhla(q, k, v, W.cuda(), q_rope=qr, k_rope=kr, normalize=normalize)
+    torch.cuda.synchronize()
+    assert not torch.isnan(out).any()
+    for (b, h) in {(0, 0), (B - 1, H - 1), (B // 2, H // 2)}:
+        sl = lambda t: None if t is None else t[b, h][None].cpu()  # noqa: E731
+        ref = oracle.blockmix_fwd(sl(q), sl(k), sl(v), W, normalize=normalize, q_rope=sl(qr), k_rope=sl(kr))
+        _check(ref[0], out[b, h], torch.bfloat16)
+
+
 def test_host_pipeline_matches_device_call():
     """mhla_host (pinned host tensors, copies and kernels pipelined over ranges of (b,h) units) is bit-identical to one
     device call on the whole batch - the units are independent."""
