@@ -65,7 +65,8 @@ struct alignas(64) BlockmixParams {
   const float* wscale;                      // [1]: power of two the mixing matrix was divided by (prep_mix_scaled_kernel)
   const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
-  int G, H, M, w, TW, nsub;
+  int G, H, M, w, TW, nsub;                 // G, M: as scheduled - with packing, G = groups / pack and M = pack * M0
+  int pack, M0;                             // small M: `pack` consecutive (b,h) groups share one 128-row mixing tile (block-diagonal W)
   int ncols, wpad;
   int n2_rows, n2_cols, n2_scols;           // P2 tile grid; first n2_scols column tiles are S columns
   int kslabs;                               // ceil(M / 64)
@@ -270,7 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         if (p.pf_dist <= 0) return;
         idx += (long long)p.pf_dist * nct13_p;
         if (idx >= n1tot_p) return;
-        const int g_ = (int)(idx / p.M), j_ = (int)(idx % p.M);
+        const int g_ = (int)(idx / p.M0), j_ = (int)(idx % p.M0);   // linear block index = real group * M0 + block
         const int b_ = g_ / p.H, h_ = g_ % p.H;
         for (int sub = 0; sub < p.nsub; ++sub)
           for (int c0 = 0; c0 < D; c0 += 64) {
@@ -301,12 +302,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         if (prof_on) w_dep += clock64() - tq0;      // time spent waiting for the scheduler (nothing ready)
         if (!more) break;
         st_release_cta_shared(q_started, sched.idx);
-        const int b = it.g / p.H, h = it.g % p.H;
+        // (packing: item (g, t) is block t % M0 of real group g * pack + t / M0)
+        const int gr = it.g * p.pack + it.t / p.M0;
+        const int b = gr / p.H, h = gr % p.H;
         trace_ev(p, 0, pitem, 0);
         if (p.prof != nullptr && (int)blockIdx.x == p.trace_cta && pitem < 256)
           p.prof[(size_t)gridDim.x * 16 + ((size_t)0 * 256 + pitem) * 4 + 3] = (unsigned long long)it.type;
         if (it.type == 1) {
-          const int j = it.t;
+          const int j = it.t % p.M0;
           for (int sub = 0; sub < p.nsub; ++sub) {
             const int t0 = sub * p.TW;
             if constexpr (D == 64) {
@@ -356,7 +359,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
           // (after this item's own loads: the TMA unit serves its queue in order)
-          prefetch_block((long long)it.g * p.M + j, true, p.normalize != 0, false);
+          prefetch_block((long long)it.g * p.M + it.t, true, p.normalize != 0, false);
         } else if (it.type == 2) {
           if (dynamic) wait_dependency();
           const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
@@ -381,7 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           }
         } else {
           if (dynamic) wait_dependency();
-          const int i = it.t;
+          const int i = it.t % p.M0;                 // block inside its real group (tensor coordinate)
+          const int irow = it.g * p.M + it.t;        // row of the block in the S~ workspace
           const CUtensorMap* tq = &p.tmQr;
           if constexpr (D == 64) {
             for (int sub = 0; sub < p.nsub; ++sub) {
@@ -389,15 +393,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               uint8_t* st = ring + r.idx() * kStageBytes;
               mbar_arrive_expect_tx(&full[r.idx()], tile_bytes + (sub == 0 ? 8192 : 0));
               tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
-              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, it.g * p.M + i, kEvictFirst);
+              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, irow, kEvictFirst);
               r.advance();
             }
           } else {
             mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
             uint8_t* st = ring + r.idx() * kStageBytes;
             mbar_arrive_expect_tx(&full[r.idx()], 32768);
-            tma_load_3d(st, &p.tmStld, &full[r.idx()], 0, 0, it.g * p.M + i, kEvictFirst);
-            tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 64, 0, it.g * p.M + i, kEvictFirst);
+            tma_load_3d(st, &p.tmStld, &full[r.idx()], 0, 0, irow, kEvictFirst);
+            tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 64, 0, irow, kEvictFirst);
             r.advance();
             for (int sub = 0; sub < p.nsub; ++sub) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
           // the readout's Q tile has not been read before unless the normaliser pulled the same tensor through L2
-          if (!p.normalize || p.ropenorm || p.mode != 0) prefetch_block((long long)it.g * p.M + i, false, false, true);
+          if (!p.normalize || p.ropenorm || p.mode != 0) prefetch_block((long long)it.g * p.M + it.t, false, false, true);
         }
         trace_ev(p, 0, pitem, 1);
         ++pitem;
@@ -835,8 +839,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       float down = 1.0f;
       if (p.is_fp16) {   // fp16 planes: normalise by a power of two (every CTA reduces the whole matrix - it is tiny)
         float amax = 0.f;
-        const int nn = p.M * p.M;
-        for (int idx = t256; idx < nn; idx += 256) amax = fmaxf(amax, fabsf(__ldg(p.mix + (long long)(idx / p.M) * p.mix_ld + idx % p.M)));
+        const int nn = p.M0 * p.M0;
+        for (int idx = t256; idx < nn; idx += 256) amax = fmaxf(amax, fabsf(__ldg(p.mix + (long long)(idx / p.M0) * p.mix_ld + idx % p.M0)));
         for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
         float* red = reinterpret_cast<float*>(smem + kSmemKsum);   // scratch: the ksum area is not in use yet
         if (lane == 0) red[warp - 4] = amax;
@@ -855,7 +859,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const int nplane = p.M * p.Mp;
       for (int row = blockIdx.x; row < p.M; row += gridDim.x)
         for (int j = t256; j < p.Mp; j += 256) {
-          const float val = j < p.M ? __ldg(p.mix + (long long)row * p.mix_ld + j) * down : 0.f;
+          // packed groups: the scheduled matrix is block-diagonal, `pack` copies of the caller's M0 x M0 matrix
+          const float val = (j < p.M && row / p.M0 == j / p.M0)
+                                ? __ldg(p.mix + (long long)(row % p.M0) * p.mix_ld + j % p.M0) * down : 0.f;
           uint16_t hi, lo;
           split16(val, hi, lo);
           p.w_planes[row * p.Mp + j] = hi;
@@ -972,8 +978,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         r.advance((wres ? 1 : 2) * p.kslabs);
         item_done();
       } else {
-        const int i = it.t;
-        const int b = it.g / p.H, h = it.g % p.H;
+        const int i = it.t;                               // block row within the scheduled (packed) group
+        const int gr = it.g * p.pack + it.t / p.M0;       // real (b,h) group and block inside it: tensor coordinates
+        const int b = gr / p.H, h = gr % p.H, ib = it.t % p.M0;
         float dsum[2] = {1.f, 1.f};
         if (p.normalize) {
           // den = mix.n_loc_hi + mix.n_loc_lo + eps was written by other CTAs; the item was only enqueued after its
@@ -1001,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             chunk_tma_begin();
             // the output is never read again: mark its lines evict-first so that they leave L2 before the Q tiles the
             // readout of later groups still needs
-            if (et == 0) tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, i, h, b, p.o_hint ? kEvictFirst : kEvictNormal);
+            if (et == 0) tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, ib, h, b, p.o_hint ? kEvictFirst : kEvictNormal);
             chunk_tma_end();
           }
         }
@@ -1107,18 +1114,19 @@ __global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, uin
 // epilogue and zero the dependency counters / item tickets.  Every block reduces the whole matrix (M*M floats,
 // L2-resident after the first touch) so that no inter-block synchronisation is needed.
 __global__ void prep_mix_scaled_kernel(const float* __restrict__ mix, long long ld, uint16_t* __restrict__ out, int M,
-                                       int Mp, int is_fp16, float* __restrict__ wscale, uint32_t* counters,
+                                       int Mp, int M0, int is_fp16, float* __restrict__ wscale, uint32_t* counters,
                                        int ncounters) {
+  // M = pack * M0: the scheduled matrix is block-diagonal with `pack` copies of the caller's M0 x M0 matrix
   grid_launch_dependents();
   // bf16 planes carry the fp32 exponent range: only fp16 needs the normalisation (and pays for the reduction)
   int e = 0;
   if (is_fp16) {
     __shared__ float red[32];
     float amax = 0.f;
-    const int nn = M * M;
+    const int nn = M0 * M0;
 #pragma unroll 4
     for (int idx = threadIdx.x; idx < nn; idx += blockDim.x)
-      amax = fmaxf(amax, fabsf(__ldg(mix + (long long)(idx / M) * ld + idx % M)));
+      amax = fmaxf(amax, fabsf(__ldg(mix + (long long)(idx / M0) * ld + idx % M0)));
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = amax;
     __syncthreads();
@@ -1133,7 +1141,7 @@ __global__ void prep_mix_scaled_kernel(const float* __restrict__ mix, long long 
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int i = idx / Mp, j = idx % Mp;
     float v = 0.f;
-    if (j < M) v = mix[(long long)i * ld + j] * down;
+    if (j < M && i / M0 == j / M0) v = mix[(long long)(i % M0) * ld + j % M0] * down;
     if (is_fp16) {
       const __half h = __float2half_rn(v);
       out[idx] = __half_as_ushort(h);

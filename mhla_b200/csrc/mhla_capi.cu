@@ -80,6 +80,7 @@ constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (sepa
 // ------------------------------------------------------------------------------------------------ blockmix
 struct BlockmixPlan {
   int G, TW, nsub, wpad, ncols, Mp, n2_rows, n2_cols, n2_scols, kslabs, normalize, ropenorm;
+  int pack, Gs, Ms;   // small M: `pack` consecutive groups are scheduled as one group of Ms = pack * M blocks (Gs = G / pack)
   size_t off_S, off_St, off_den, off_W, off_cnt, total;
 };
 
@@ -89,7 +90,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   if (d->B < 1 || d->H < 1 || d->M < 1 || d->w < 1) return MHLA_ERR_UNSUPPORTED_SHAPE;
   if (d->D != 64 && d->D != 128) return MHLA_ERR_UNSUPPORTED_SHAPE;
   if (d->w > 256) return MHLA_ERR_UNSUPPORTED_SHAPE;
-  if ((long long)d->B * d->H > 16383 || d->M > 65535) return MHLA_ERR_UNSUPPORTED_SHAPE;   // item FIFO field widths
+  if ((long long)d->B * d->H > 16383 * 8 || d->M > 65535) return MHLA_ERR_UNSUPPORTED_SHAPE;   // item FIFO field widths (checked again below)
   const int D = d->D;
   pl->G = d->B * d->H;
   pl->TW = d->w >= 128 ? 128 : (d->w + 15) / 16 * 16;
@@ -98,17 +99,27 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->ropenorm = (pl->normalize && d->k_rope.ptr != nullptr) ? 1 : 0;
   pl->wpad = pl->normalize ? (pl->nsub * pl->TW) : 0;
   pl->ncols = D * D + 2 * pl->wpad;          // 16-bit elements: S_j | n_loc hi | n_loc lo
-  pl->Mp = (d->M + 7) / 8 * 8;
-  pl->n2_rows = (d->M + 127) / 128;
+  // Small block counts waste the 128-row mixing tile: schedule `pack` consecutive (b,h) groups as ONE group whose
+  // mixing matrix is block-diagonal (pack copies of the caller's matrix).  Their rows are consecutive in the workspace,
+  // so nothing else changes; pack must divide the number of groups.
+  pl->pack = 1;
+  if (!std::getenv("MHLA_NO_PACK"))
+    for (int pk = 128 / d->M; pk >= 2; --pk)
+      if (pl->G % pk == 0) { pl->pack = pk; break; }
+  pl->Gs = pl->G / pl->pack;
+  if (pl->Gs > 16383) return MHLA_ERR_UNSUPPORTED_SHAPE;   // item FIFO: 14-bit group field
+  pl->Ms = d->M * pl->pack;
+  pl->Mp = (pl->Ms + 7) / 8 * 8;
+  pl->n2_rows = (pl->Ms + 127) / 128;
   pl->n2_scols = D * D / 256;
   pl->n2_cols = pl->n2_scols + (2 * pl->wpad + 255) / 256;
-  pl->kslabs = (d->M + 63) / 64;
+  pl->kslabs = (pl->Ms + 63) / 64;
   size_t off = 0;
   const size_t GM = (size_t)pl->G * d->M;
   pl->off_S = off;   off = align_up(off + GM * pl->ncols * 2, 1024);
   pl->off_St = off;  off = align_up(off + GM * D * D * 2, 1024);
   pl->off_den = off; off = align_up(off + GM * (pl->wpad ? 2 * pl->wpad : 32) * 4, 1024);
-  pl->off_W = off;   off = align_up(off + (size_t)2 * d->M * pl->Mp * 2, 1024);
+  pl->off_W = off;   off = align_up(off + (size_t)2 * pl->Ms * pl->Mp * 2, 1024);
   pl->off_cnt = off; off = align_up(off + ((size_t)2 * pl->G * kCntStride + 128) * 4, 1024);   // + item tickets, flags
   pl->total = off;
   return MHLA_OK;
@@ -174,24 +185,24 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
     if (!encode_map(&P->tmSst, s)) return MHLA_ERR_CUDA;
   }
   {
-    MapSpec s{dt16, 3, S, {(uint64_t)pl.ncols, (uint64_t)d->M, (uint64_t)pl.G},
-              {(uint64_t)pl.ncols * 2, (uint64_t)d->M * pl.ncols * 2}, {64, 64, 1}};
+    MapSpec s{dt16, 3, S, {(uint64_t)pl.ncols, (uint64_t)pl.Ms, (uint64_t)pl.Gs},
+              {(uint64_t)pl.ncols * 2, (uint64_t)pl.Ms * pl.ncols * 2}, {64, 64, 1}};
     if (!encode_map(&P->tmSld, s)) return MHLA_ERR_CUDA;
   }
   {
-    MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)d->M, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)d->M * pl.Mp * 2},
+    MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)pl.Ms, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)pl.Ms * pl.Mp * 2},
               {64, 128, 1}};
     if (!encode_map(&P->tmW, s)) return MHLA_ERR_CUDA;
   }
   {
-    MapSpec s{dt16, 3, St, {(uint64_t)D * D, (uint64_t)d->M, (uint64_t)pl.G},
-              {(uint64_t)D * D * 2, (uint64_t)d->M * D * D * 2}, {64, 128, 1}};
+    MapSpec s{dt16, 3, St, {(uint64_t)D * D, (uint64_t)pl.Ms, (uint64_t)pl.Gs},
+              {(uint64_t)D * D * 2, (uint64_t)pl.Ms * D * D * 2}, {64, 128, 1}};
     if (!encode_map(&P->tmStst, s)) return MHLA_ERR_CUDA;
   }
   {
     const uint64_t wp = pl.wpad ? 2 * pl.wpad : 32;
-    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, den, {wp, (uint64_t)d->M, (uint64_t)pl.G},
-              {wp * 4, (uint64_t)d->M * wp * 4}, {32, 128, 1}};
+    MapSpec s{CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, den, {wp, (uint64_t)pl.Ms, (uint64_t)pl.Gs},
+              {wp * 4, (uint64_t)pl.Ms * wp * 4}, {32, 128, 1}};
     if (!encode_map(&P->tmDen, s)) return MHLA_ERR_CUDA;
   }
   {
@@ -203,9 +214,9 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->ws_St = reinterpret_cast<uint16_t*>(St);
   P->den = den;
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
-  P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.G * kCntStride + 48);
+  P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.Gs * kCntStride + 48);
   P->mix = d->mix; P->mix_ld = d->mix_ld; P->w_planes = Wp; P->Mp = pl.Mp; P->self_prep = 0;
-  P->G = pl.G; P->H = d->H; P->M = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
+  P->G = pl.Gs; P->H = d->H; P->M = pl.Ms; P->pack = pl.pack; P->M0 = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
   P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
   P->normalize = pl.normalize; P->ropenorm = pl.ropenorm; P->is_fp16 = d->dtype == MHLA_FP16;
@@ -332,13 +343,13 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.self_prep = (single && (d->flags & MHLA_FLAG_WS_PERSISTENT) && !std::getenv("MHLA_NO_SELF_PREP")) ? 1 : 0;
   if (!P.self_prep) {
     mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
-                                                       reinterpret_cast<uint16_t*>(ws + pl.off_W), d->M, pl.Mp,
+                                                       reinterpret_cast<uint16_t*>(ws + pl.off_W), pl.Ms, pl.Mp, d->M,
                                                        d->dtype == MHLA_FP16, const_cast<float*>(P.wscale), P.counters,
-                                                       2 * pl.G * kCntStride + 48);
+                                                       2 * pl.Gs * kCntStride + 48);
     // (words 48.. of the tail: wscale and the self_prep flags - the prologue kernel leaves them alone)
     ++launches;
   }
-  const long long n1 = d->M, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = d->M;
+  const long long n1 = pl.Ms, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = pl.Ms;
   auto launch_pdl = [&](int grid) -> bool {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
@@ -372,7 +383,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
       P.ring_stages = small_staging ? 6 : 5;
       P.slots_per_wg = 2;
       if (P.mode == 4 && P.np2 < 0) P.np2 = 0;
-      const long long items = (long long)pl.G * (P.mode == 4 ? n1 + n2 : (mode == 1 ? n1 : (mode == 2 ? n2 : n3)));
+      const long long items = (long long)pl.Gs * (P.mode == 4 ? n1 + n2 : (mode == 1 ? n1 : (mode == 2 ? n2 : n3)));
       if (P.mode != 4 && P.mode != 0) P.np2 = 0;
       const int grid = (int)(items < g_num_sms ? items : g_num_sms);
       if (P.np2 > grid / 2) P.np2 = grid / 2;
@@ -387,7 +398,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     P.slots_per_wg = 2;
     if (const char* e = std::getenv("MHLA_SLOTS")) P.slots_per_wg = std::atoi(e) == 1 ? 1 : 2;
     P.ring_stages = P.slots_per_wg == 1 ? 6 : 5;   // one staging slot per warpgroup buys a sixth ring stage
-    const long long items = (long long)pl.G * (n1 + n2 + n3);
+    const long long items = (long long)pl.Gs * (n1 + n2 + n3);
     const int grid = (int)(items < g_num_sms ? items : g_num_sms);
     // dedicated block-mixing CTAs: one per P2 tile of a group, when that leaves most of the grid for streaming
     if (P.np2 < 0) P.np2 = 0;   // (dedicated mixing CTAs are a tuning option: MHLA_NP2)
