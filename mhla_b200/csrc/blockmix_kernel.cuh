@@ -81,6 +81,7 @@ struct alignas(64) BlockmixParams {
   int slots_per_wg;                         // staging slots per epilogue warpgroup (2, or 1 to buy another ring stage)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
   int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
+  int q_hint;                               // 1: evict-first on the normaliser's Q loads when the readout comes much later
   int o_hint;                               // 1: evict-first L2 hint on the output stores
   int policy;                               // mode 0: 0 = ready P3 items before new P1 items (window), 1 = P3 items last
   int reverse3;                             // mode 3: walk the groups backwards
@@ -261,6 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       // A dependent item is only enqueued after the scheduler lane has acquired its group's counter; the FIFO hand-off
       // (release/acquire in shared memory) extends that to this lane, the proxy fence to the TMA loads issued below.
       auto wait_dependency = [&]() { fence_proxy_async_all(); };
+      // Q tiles of the normaliser: worth keeping in L2 only if the readout follows within a few groups (policy 0)
+      const uint64_t q_hint = (p.mode == 0 && p.policy == 0) ? kEvictLast : (p.q_hint ? kEvictFirst : kEvictNormal);
       // The streaming items a CTA owns are a fixed arithmetic sequence of linear block indices, so the producer can pull
       // the tiles of the item `pf_dist` places further down its own list into L2 while it fills shared memory for the
       // current one: the shared-memory fill then sees L2 latency instead of HBM latency, and the bytes in flight towards
@@ -345,15 +348,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               uint8_t* st = ring + r.idx() * kStageBytes;
               mbar_arrive_expect_tx(&full[r.idx()], p.nsub * tile_bytes);
               for (int sub = 0; sub < p.nsub; ++sub)
-                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, kEvictLast);
+                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, q_hint);
               r.advance();
             } else {
               for (int sub = 0; sub < p.nsub; ++sub) {
                 mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
                 uint8_t* st = ring + r.idx() * kStageBytes;
                 mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
-                tma_load_5d(st, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, kEvictLast);
-                tma_load_5d(st + 16384, &p.tmQn, &full[r.idx()], 64, sub * p.TW, j, h, b, kEvictLast);
+                tma_load_5d(st, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, q_hint);
+                tma_load_5d(st + 16384, &p.tmQn, &full[r.idx()], 64, sub * p.TW, j, h, b, q_hint);
                 r.advance();
               }
             }

@@ -318,6 +318,8 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (const char* e = std::getenv("MHLA_MIX_HI_ONLY")) P.mix_hi_only = std::atoi(e);
   P.policy = 1;
   P.o_hint = 1;
+  P.q_hint = 1;
+  if (const char* e = std::getenv("MHLA_QHINT")) P.q_hint = std::atoi(e);
   if (const char* e = std::getenv("MHLA_OHINT")) P.o_hint = std::atoi(e);
   if (const char* e = std::getenv("MHLA_POLICY")) P.policy = std::atoi(e);
   P.pf_dist = 0;

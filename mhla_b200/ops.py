@@ -175,6 +175,7 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
 
 
 _HOST_STREAMS: "dict[int, tuple]" = {}
+_HOST_BUFS: "dict[tuple, tuple]" = {}
 
 
 def mhla_host(q, k, v, mix, *, out: Optional[torch.Tensor] = None, device=None, eps: float = 1e-6, normalize: bool = True,
@@ -201,8 +202,15 @@ def mhla_host(q, k, v, mix, *, out: Optional[torch.Tensor] = None, device=None, 
             s_.wait_stream(cur)
         mix_d = mix.to(dev, non_blocking=True) if not mix.is_cuda else mix
         s_run.wait_stream(cur)
-        dq = torch.empty((units, 1, M, w, D), dtype=q.dtype, device=dev)
-        dk, dv, do = torch.empty_like(dq), torch.empty_like(dq), torch.empty_like(dq)
+        # device staging buffers are kept per shape: every call orders itself after the previous one through the
+        # caller's stream (first and last statements of this block), so reuse is safe and no allocator traffic is left
+        bkey = (dev.index, units, M, w, D, q.dtype)
+        bufs = _HOST_BUFS.get(bkey)
+        if bufs is None:
+            if len(_HOST_BUFS) >= 2:
+                _HOST_BUFS.pop(next(iter(_HOST_BUFS)))
+            bufs = _HOST_BUFS[bkey] = tuple(torch.empty((units, 1, M, w, D), dtype=q.dtype, device=dev) for _ in range(4))
+        dq, dk, dv, do = bufs
         per = (units + chunks - 1) // chunks
         for c in range(chunks):
             lo, hi = c * per, min(units, (c + 1) * per)
@@ -223,8 +231,6 @@ def mhla_host(q, k, v, mix, *, out: Optional[torch.Tensor] = None, device=None, 
                 s_out.wait_event(ev_run)
                 of[lo:hi].copy_(do[lo:hi], non_blocking=True)
         cur.wait_stream(s_out)
-        for t in (dq, dk, dv, do):
-            t.record_stream(s_in); t.record_stream(s_run); t.record_stream(s_out)
     return out
 
 
