@@ -1089,13 +1089,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 // Tiny prologue: split the fp32 mixing matrix into hi + lo 16-bit planes [2][M][Mp] (optionally keeping only the
 // strictly-lower triangle and folding a scale, for the causal variant) and zero the dependency counters.
 __global__ void prep_mix_kernel(const float* __restrict__ mix, long long ld, uint16_t* __restrict__ out, int M, int Mp,
-                                int strict_lower, float scale, int is_fp16, uint32_t* counters, int ncounters) {
+                                int M0, int strict_lower, float scale, int is_fp16, uint32_t* counters, int ncounters) {
   grid_launch_dependents();   // the main kernel may start its prologue now; it waits (griddepcontrol.wait) for our results
+  // M = pack * M0: block-diagonal, `pack` copies of the caller's M0 x M0 matrix (packing of consecutive (b,h) groups)
   const int n = M * Mp;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += gridDim.x * blockDim.x) {
     const int i = idx / Mp, j = idx % Mp;
     float v = 0.f;
-    if (j < M && (!strict_lower || j < i)) v = mix[(long long)i * ld + j] * scale;
+    if (j < M && i / M0 == j / M0 && (!strict_lower || j % M0 < i % M0)) v = mix[(long long)(i % M0) * ld + j % M0] * scale;
     uint16_t hi, lo;
     if (is_fp16) {
       const __half h = __float2half_rn(v);

@@ -32,7 +32,8 @@ struct alignas(64) CausalParams {
   const float* mm;                 // original fp32 mixing matrix (diagonal is read by the epilogue)
   long long mm_ld;
   uint32_t* counters;              // [2*G]
-  int G, H, n;
+  int G, H, n;                     // as scheduled: with packing G = groups / pack, n = pack * n0
+  int pack, n0;                    // `pack` consecutive (b,h) groups share one 128-row mixing tile (block-diagonal mm)
   int n2_rows, n2_cols, kslabs;
   int is_fp16, mode, lag2, lag3;
   float scale;
@@ -119,9 +120,12 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
     if (elect_one()) {
       Ring r;
       while (sched.next(it)) {
-        const int b = it.g / p.H, h = it.g % p.H;
+        // (packing: scheduled chunk c of scheduled group g is chunk c % n0 of real group g * pack + c / n0)
+        const int cs = it.type == 3 ? it.t / NVH : it.t;
+        const int gr = it.g * p.pack + cs / p.n0;
+        const int b = gr / p.H, h = gr % p.H;
         if (it.type == 1) {
-          const int j = it.t;
+          const int j = it.t % p.n0;
           mbar_wait(&empty[r.stage], r.phase ^ 1);
           uint8_t* st = ring + r.stage * kStageBytes;
           mbar_arrive_expect_tx(&full[r.stage], (kKVOneStage ? (DK + DV) / 64 : DK / 64) * kCTile);
@@ -159,7 +163,8 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
             spin_until(&p.counters[p.G + it.g], (uint32_t)(p.n2_rows * p.n2_cols));
             fence_proxy_async_all();
           }
-          const int i = it.t / NVH, vh = it.t % NVH;
+          const int is = it.t / NVH, vh = it.t % NVH;   // is: scheduled chunk (workspace row), i: chunk in its real group
+          const int i = is % p.n0;
           // stage A: q tiles | k tiles
           mbar_wait(&empty[r.stage], r.phase ^ 1);
           uint8_t* st = ring + r.stage * kStageBytes;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
           st = ring + r.stage * kStageBytes;
           mbar_arrive_expect_tx(&full[r.stage], (DVH / 64) * DK * 128);
           for (int c = 0; c < DVH / 64; ++c)
-            tma_load_3d(st + c * DK * 128, &p.tmStld, &full[r.stage], vh * DVH + c * 64, 0, it.g * p.n + i, kEvictFirst);
+            tma_load_3d(st + c * DK * 128, &p.tmStld, &full[r.stage], vh * DVH + c * 64, 0, it.g * p.n + is, kEvictFirst);
           r.advance();
         }
       }
@@ -386,7 +391,9 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
           red_release_gpu_add(&p.counters[p.G + it.g], 1u);
         }
       } else {
-        const int i = it.t / NVH, vh = it.t % NVH;
+        const int is = it.t / NVH, vh = it.t % NVH;
+        const int i = is % p.n0;                          // chunk inside its real group
+        const int gr = it.g * p.pack + is / p.n0;         // real (b,h) group
         const Ring rB = r.at(1);
         const float dscale = p.scale * __ldg(p.mm + (long long)i * p.mm_ld + i);
         // ---- masked P: TMEM -> registers -> 16-bit K-major swizzled tile in stage B (+16 KB)
@@ -423,7 +430,7 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
           if (row64_ok) stage_row(buf, row64, pk);
           staging_publish();
           if (et == 0) {
-            const int b = it.g / p.H, h = it.g % p.H;
+            const int b = gr / p.H, h = gr % p.H;
             tma_store_5d(&p.tmO, buf, vh * DVH + c * 64, 0, i, h, b);
             tma_store_commit();
           }
@@ -446,6 +453,7 @@ __global__ void __launch_bounds__(kCausalThreads, 1) causal_kernel(const __grid_
 // ---------------------------------------------------------------------------------------------------- host side
 struct CausalPlan {
   int G, n, Mp, n2_rows, n2_cols, kslabs;
+  int pack, Gs, ns;   // scheduled groups / chunks per scheduled group (packing of consecutive (b,h) groups)
   size_t off_S, off_St, off_W, off_cnt, total;
 };
 
@@ -460,16 +468,22 @@ inline int plan_causal(const mhla_causal_desc* d, CausalPlan* pl) {
   pl->G = d->B * d->H;
   pl->n = d->T / kChunk;
   if (pl->n > d->L) return MHLA_ERR_INVALID_ARGUMENT;
-  pl->Mp = (pl->n + 7) / 8 * 8;
-  pl->n2_rows = (pl->n + 127) / 128;
+  // few chunks per sequence: schedule `pack` consecutive (b,h) groups as one group with a block-diagonal mixing matrix
+  pl->pack = 1;
+  for (int pk = 128 / pl->n; pk >= 2; --pk)
+    if (pl->G % pk == 0) { pl->pack = pk; break; }
+  pl->Gs = pl->G / pl->pack;
+  pl->ns = pl->n * pl->pack;
+  pl->Mp = (pl->ns + 7) / 8 * 8;
+  pl->n2_rows = (pl->ns + 127) / 128;
   pl->n2_cols = d->K * d->V / 256;
-  pl->kslabs = (pl->n + 63) / 64;
+  pl->kslabs = (pl->ns + 63) / 64;
   const size_t Gn = (size_t)pl->G * pl->n, KV = (size_t)d->K * d->V;
   auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
   size_t off = 0;
   pl->off_S = off;   off = up(off + Gn * KV * 2);
   pl->off_St = off;  off = up(off + Gn * KV * 2);
-  pl->off_W = off;   off = up(off + (size_t)2 * pl->n * pl->Mp * 2);
+  pl->off_W = off;   off = up(off + (size_t)2 * pl->ns * pl->Mp * 2);
   pl->off_cnt = off; off = up(off + (size_t)2 * pl->G * 4);
   pl->total = off;
   return MHLA_OK;
@@ -494,17 +508,17 @@ inline int causal_launch(CausalParams& P, const CausalPlan& pl, int unfused, int
     attr = true;
   }
   constexpr int NVH = DV > 128 ? DV / 128 : 1;
-  const long long n1 = pl.n, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = (long long)pl.n * NVH;
+  const long long n1 = pl.ns, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = (long long)pl.ns * NVH;
   if (unfused) {
     for (int mode = 1; mode <= 3; ++mode) {
       P.mode = mode;
-      const long long items = (long long)pl.G * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
+      const long long items = (long long)pl.Gs * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
       kern<<<(int)(items < num_sms ? items : num_sms), kCausalThreads, kSmemAlloc, stream>>>(P);
       ++*launches;
     }
   } else {
     P.mode = 0;
-    const long long items = (long long)pl.G * (n1 + n2 + n3);
+    const long long items = (long long)pl.Gs * (n1 + n2 + n3);
     kern<<<(int)(items < num_sms ? items : num_sms), kCausalThreads, kSmemAlloc, stream>>>(P);
     ++*launches;
   }

@@ -468,7 +468,7 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
       void* S = ws + pl.off_S;
       void* St = ws + pl.off_St;
       void* Wp = ws + pl.off_W;
-      const uint64_t Gn = (uint64_t)pl.G * pl.n, KV = (uint64_t)d->K * d->V;
+      const uint64_t Gn = (uint64_t)pl.G * pl.n, KV = (uint64_t)d->K * d->V;   // = Gs * ns: rows of consecutive groups
       auto t4 = [&](const mhla_tensor4& t, int dim) {
         // [B, T, H, dim] viewed as (dim, 64, n, H, B)
         MapSpec s{};
@@ -498,19 +498,19 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
         if (!encode_map(&P.tmStld, s)) return MHLA_ERR_CUDA;
       }
       {
-        MapSpec s{dt16, 3, S, {KV, (uint64_t)pl.n, (uint64_t)pl.G}, {KV * 2, (uint64_t)pl.n * KV * 2}, {64, 64, 1}};
+        MapSpec s{dt16, 3, S, {KV, (uint64_t)pl.ns, (uint64_t)pl.Gs}, {KV * 2, (uint64_t)pl.ns * KV * 2}, {64, 64, 1}};
         if (!encode_map(&P.tmSld, s)) return MHLA_ERR_CUDA;
         s.base = St; s.box[1] = 128;
         if (!encode_map(&P.tmStst, s)) return MHLA_ERR_CUDA;
       }
       {
-        MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)pl.n, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)pl.n * pl.Mp * 2},
+        MapSpec s{dt16, 3, Wp, {(uint64_t)pl.Mp, (uint64_t)pl.ns, 2}, {(uint64_t)pl.Mp * 2, (uint64_t)pl.ns * pl.Mp * 2},
                   {64, 128, 1}};
         if (!encode_map(&P.tmW, s)) return MHLA_ERR_CUDA;
       }
       P.mm = d->mm; P.mm_ld = d->mm_ld;
       P.counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
-      P.G = pl.G; P.H = d->H; P.n = pl.n;
+      P.G = pl.Gs; P.H = d->H; P.n = pl.ns; P.pack = pl.pack; P.n0 = pl.n;
       P.n2_rows = pl.n2_rows; P.n2_cols = pl.n2_cols; P.kslabs = pl.kslabs;
       P.is_fp16 = d->dtype == MHLA_FP16; P.mode = 0; P.lag2 = 1; P.lag3 = 3;
       P.scale = d->scale;
@@ -524,7 +524,7 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
   mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mm, (long long)d->mm_ld, reinterpret_cast<uint16_t*>(ws + pl.off_W),
-                                               pl.n, pl.Mp, 1, d->scale, d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
+                                               pl.ns, pl.Mp, pl.n, 1, d->scale, d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
   ++launches;
   const int unfused = (d->flags & MHLA_FLAG_UNFUSED) ? 1 : 0;
   rc = MHLA_ERR_UNSUPPORTED_SHAPE;
