@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MHLA_B200_ABI_VERSION 1
+#define MHLA_B200_ABI_VERSION 2
 
 typedef enum mhla_status {
   MHLA_OK = 0,
@@ -93,6 +93,11 @@ typedef struct mhla_blockmix_desc {
   int64_t mix_ld;
   void* workspace;       /* >= mhla_blockmix_workspace_bytes(desc) bytes, 1024-byte aligned */
   size_t workspace_bytes;
+  /* Optional fused epilogue: per-(token, head) RMS normalisation of the output row,
+   * out = o * rsqrt(mean_d(o^2) + out_rms_eps) * out_rms_weight[d]  - the per-head `g_norm` of MHLA_Video_Uni
+   * (mhla_videogen/diffusion/model/wan/mhla_utils.py:360-362, WanRMSNorm wan/model.py:181-196).  NULL: off. */
+  const float* out_rms_weight; /* [D] fp32 device pointer or NULL */
+  float out_rms_eps;
 } mhla_blockmix_desc;
 
 size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);

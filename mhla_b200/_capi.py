@@ -36,6 +36,7 @@ class BlockmixDesc(C.Structure):
         ("dtype", C.c_int32), ("flags", C.c_uint32), ("eps", C.c_float),
         ("q", Tensor5), ("k", Tensor5), ("v", Tensor5), ("q_rope", Tensor5), ("k_rope", Tensor5), ("out", Tensor5),
         ("mix", C.c_void_p), ("mix_ld", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+        ("out_rms_weight", C.c_void_p), ("out_rms_eps", C.c_float),
     ]
 
 
@@ -86,7 +87,7 @@ def lib() -> C.CDLL:
         L.mhla_causal_workspace_bytes.argtypes = [C.POINTER(CausalDesc)]
         L.mhla_fwd_causal.restype = C.c_int
         L.mhla_fwd_causal.argtypes = [C.POINTER(CausalDesc), C.c_void_p]
-        if L.mhla_abi_version() != 1:
+        if L.mhla_abi_version() != 2:
             raise ImportError("libmhla_b200.so ABI version mismatch; rebuild with `python -m mhla_b200.build --force`")
         _lib = L
     return _lib

@@ -3,20 +3,20 @@
 // Replaces the inline PyTorch operator of the reference:
 //   mhla_dit/mhla/mhla.py:262-268 and mhla_videogen/diffusion/model/wan/mhla_utils.py:328-341.
 //
-// Work is cut into three kinds of items that flow through one TMA->smem ring, one tcgen05 issuer and one
-// epilogue warpgroup (see DESIGN.md "Kernel"):
+// Work is cut into three kinds of items that flow through one TMA->smem ring, one tcgen05 issuer and two
+// epilogue warpgroups:
 //   P1 (g, j)        S_j = K_j^T V_j  (+ ksum_j via an all-ones B operand, n_loc[j,t] = q_{j,t}.ksum_j)
 //   P2 (g, it, ic)   [S~ | den] rows it*128.., cols ic*256.. = mix . [S | n_loc]    (GEMM over blocks; S is kept
 //                    in 16-bit, mix and n_loc are split hi+lo so the product carries ~16 mantissa bits.  A TF32
 //                    formulation is not possible: tcgen05 kind::tf32 returns zeros for an MN-major operand with
 //                    the plain 128B swizzle - see profiles/r01_microtest_umma_layouts.log)
 //   P3 (g, i)        O_i = (Q_i S~_i) / den_i
-// Every item has a fixed owner CTA (linear item index mod grid size), but the ORDER in which a CTA runs its P1 / P2 /
-// P3 items is decided at run time by a scheduler warp: a dependent item (P2 needs all P1 of its group, P3 all P2) is
-// only enqueued once its group's arrival counter in global memory (release/acquire) says it is ready, ready P2 and
-// P3 items go before new P1 items, and P1 may run at most `window` groups ahead of the CTA's next P3 item - so the
-// S / S~ / den workspace and the second read of Q are served from L2 and no role ever blocks on a dependency.
-// The scheduler feeds the other roles through a small FIFO in shared memory; all CTAs are co-resident.
+// Items are handed out through global tickets and the ORDER in which a CTA runs them is decided at run time by a
+// scheduler warp: a dependent item (P2 needs all P1 of its group, P3 all P2) is only enqueued once its group's arrival
+// counter in global memory (release/acquire) says it is ready, so no role ever blocks on a dependency.  Default
+// policy: ready P2 items first, then P1, the readout (P3) last; `policy 0` puts ready P3 items before new P1 items
+// within a window of groups (keeps Q in L2, but stalls on the P1 -> P2 -> P3 latency chain).  The scheduler feeds the
+// other roles through a small FIFO in shared memory; all CTAs are co-resident (grid <= #SMs, 1 CTA/SM).
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -62,6 +62,8 @@ struct alignas(64) BlockmixParams {
   uint16_t* w_planes;                       // [2][M][Mp] hi | lo planes of the mixing matrix (I/O type)
   int Mp, self_prep;                        // self_prep: no prologue kernel - the CTAs split the matrix and the last one to
                                             // finish re-zeroes the control block (persistent, library-owned workspace)
+  const float* rms_w;                       // optional fused output RMSNorm weight [D] (NULL: off)
+  float rms_eps;
   const float* wscale;                      // [1]: power of two the mixing matrix was divided by (prep_mix_scaled_kernel)
   const float* den;                         // [G*M][2*wpad]: mix . n_loc_hi | mix . n_loc_lo
   uint32_t* counters;                       // [2*G]: finished P1 items, finished P2 items per group
@@ -80,7 +82,6 @@ struct alignas(64) BlockmixParams {
   int mix_hi_only;                          // bf16: S columns of the block mixing take the 8-bit hi plane only (MHLA_FLAG_FAST_MIX)
   int slots_per_wg;                         // staging slots per epilogue warpgroup (2, or 1 to buy another ring stage)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
-  int sig_mode;                             // tuning: 0 = deferred completion signals, 1 = drain after every item
   int q_hint;                               // 1: evict-first on the normaliser's Q loads when the readout comes much later
   int o_hint;                               // 1: evict-first L2 hint on the output stores
   int policy;                               // mode 0: 0 = ready P3 items before new P1 items (window), 1 = P3 items last
@@ -199,9 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint64_t* empty = full + kMaxStages;
   uint64_t* tfull = empty + kMaxStages;
   uint64_t* tempty = tfull + 2;
-  uint64_t* sfull = tempty + 2;    // staging buffer written by the epilogue warps   (epilogue -> store warp)
-  uint64_t* sfree = sfull + 2;     // staging buffer read out by TMA                 (store warp -> epilogue)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint32_t* q_published = tmem_slot + 1;   // items the scheduler warp (warp 2) has enqueued
   uint32_t* q_started = tmem_slot + 2;     // items the producer has picked up (throttles the scheduler's run-ahead)
   uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished by each epilogue warpgroup
@@ -223,7 +222,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); mbar_init(&sfull[i], 4); mbar_init(&sfree[i], 1);
+      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
     }
     fence_barrier_init();
     *q_published = 0;
@@ -803,6 +802,26 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
       if (prof_on) t_pack += clock64() - t0;
     };
+    // same with a per-column weight (fused output RMSNorm)
+    auto load_pack64_w = [&](uint32_t taddr, float scale, const float* wcol, uint32_t* pk) {
+      uint32_t v2[32];
+      tmem_ld_x32(taddr, v);
+      tmem_ld_x32(taddr + 32, v2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const float a = __uint_as_float(v[2 * e]) * scale * __ldg(wcol + 2 * e);
+        const float bq = __uint_as_float(v[2 * e + 1]) * scale * __ldg(wcol + 2 * e + 1);
+        const float c2 = __uint_as_float(v2[2 * e]) * scale * __ldg(wcol + 32 + 2 * e);
+        const float d2 = __uint_as_float(v2[2 * e + 1]) * scale * __ldg(wcol + 32 + 2 * e + 1);
+        if (p.is_fp16) {
+          __half2 h0 = __floats2half2_rn(a, bq), h1 = __floats2half2_rn(c2, d2);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h0); pk[16 + e] = *reinterpret_cast<uint32_t*>(&h1);
+        } else {
+          pk[e] = pack_bf16x2(a, bq); pk[16 + e] = pack_bf16x2(c2, d2);
+        }
+      }
+    };
     // x = hi + lo with hi, lo in the 16-bit I/O type
     auto split16 = [&](float x, uint16_t& hi, uint16_t& lo) {
       if (p.is_fp16) {
@@ -1002,10 +1021,28 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           if (sub >= p.nsub) break;
-          const float rden = p.normalize ? 1.0f / dsum[sub] : 1.0f;
+          float rden = p.normalize ? 1.0f / dsum[sub] : 1.0f;
+          if (p.rms_w != nullptr) {
+            // fused per-(token, head) RMS normalisation: first pass over the row's D accumulator columns for the sum of
+            // squares (TMEM reads are cheap), the scale then rides along with the normaliser in the second pass
+            float ss = 0.f;
+            for (int c = 0; c < D / 64; ++c) {
+              uint32_t v2[32];
+              tmem_ld_x32(acc + sub * 128 + c * 64, v);
+              tmem_ld_x32(acc + sub * 128 + c * 64 + 32, v2);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) {
+                const float a = __uint_as_float(v[e]) * rden, b2 = __uint_as_float(v2[e]) * rden;
+                ss = fmaf(a, a, ss); ss = fmaf(b2, b2, ss);
+              }
+            }
+            rden *= rsqrtf(ss * (1.0f / D) + p.rms_eps);
+          }
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
-            load_pack64(acc + sub * 128 + c * 64, rden, pk);
+            if (p.rms_w != nullptr) load_pack64_w(acc + sub * 128 + c * 64, rden, p.rms_w + c * 64, pk);
+            else load_pack64(acc + sub * 128 + c * 64, rden, pk);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_tma_begin();

@@ -215,6 +215,7 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->den = den;
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
   P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.Gs * kCntStride + 48);
+  P->rms_w = d->out_rms_weight; P->rms_eps = d->out_rms_eps;
   P->mix = d->mix; P->mix_ld = d->mix_ld; P->w_planes = Wp; P->Mp = pl.Mp; P->self_prep = 0;
   P->G = pl.Gs; P->H = d->H; P->M = pl.Ms; P->pack = pl.pack; P->M0 = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
@@ -308,8 +309,6 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   }
 
   P.prof = g_prof_buffer;
-  P.sig_mode = 0;
-  if (const char* e = std::getenv("MHLA_SIGMODE")) P.sig_mode = std::atoi(e);
   if (const char* e = std::getenv("MHLA_WINDOW")) P.window = std::atoi(e);       // tuning knobs of the fused kernel's
   if (const char* e = std::getenv("MHLA_RUNAHEAD")) P.run_ahead = std::atoi(e);  // run-time scheduler
   P.np2 = -1;

@@ -90,6 +90,7 @@ class MHLA_Video_Uni(nn.Module):
         self.g_fn = nn.SiLU() if is_gated else None
         self.g_norm = WanRMSNorm(dim_head, eps=eps)
         self.is_gated = is_gated
+        self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: g_norm inside the kernel epilogue
         self.is_lepe = is_lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
@@ -146,14 +147,18 @@ class MHLA_Video_Uni(nn.Module):
         pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
         kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
         blk = lambda t: rearrange(t.to(cdtype), pat, **kw).contiguous()           # noqa: E731  (:317-326, one 16-bit copy each)
+        # the per-head g_norm (:360-364) is fused into the kernel's readout epilogue (fp32, before the single rounding)
+        fuse = dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps) if self.fuse_out_norm else {}
         if self.normalize_out:
             out = mhla_blockmix(blk(q), blk(k), blk(v), self.block_attn.conv.weight, q_rope=blk(q_rope),
-                                k_rope=blk(k_rope), eps=self.eps, normalize=True)
+                                k_rope=blk(k_rope), eps=self.eps, normalize=True, **fuse)
         else:  # shipped Wan config (norm_output: false): the un-roped q/k are not needed at all
             out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), self.block_attn.conv.weight, eps=self.eps,
-                                normalize=False)
+                                normalize=False, **fuse)
         out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
-        out = self.g_norm(out).reshape(B, N, C)                                     # :360-364 per-head RMSNorm
+        if not self.fuse_out_norm:
+            out = self.g_norm(out)                                                  # :360-364 per-head RMSNorm
+        out = out.reshape(B, N, C)
         if self.is_gated:
             out = out * self.g_fn(self.g(x))
         if self.is_lepe:

@@ -84,7 +84,8 @@ def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
 
 def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                   out: Optional[torch.Tensor] = None, fused: bool = True, unfused: Optional[bool] = None,
-                  three_launch: bool = False, two_launch: bool = False, debug_flags: int = 0) -> torch.Tensor:
+                  three_launch: bool = False, two_launch: bool = False, debug_flags: int = 0,
+                  out_rms_weight: Optional[torch.Tensor] = None, out_rms_eps: float = 1e-6) -> torch.Tensor:
     """Non-causal block-mixed MHLA forward on block-major tensors.
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
@@ -92,6 +93,8 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
               stride is a multiple of 8 elements.
     mix     : [M, M] (or the Conv2d weight [M, M, 1, 1]); out_i = sum_j mix[i, j] (.)_j.
     q_rope, k_rope : roped copies for the numerator (variant B); q, k then only feed the normaliser.
+    out_rms_weight : optional [D] weight of a per-(token, head) RMSNorm fused into the readout epilogue
+              (out = o * rsqrt(mean_d(o^2) + out_rms_eps) * weight; MHLA_Video_Uni's g_norm, mhla_utils.py:360-362).
     fused   : (default) one persistent kernel: items are scheduled at run time, cross-CTA dependencies go through
               per-group counters.  ``three_launch`` / ``unfused=True`` run the phases as three PDL-chained launches of
               the same kernel (an independent cross-check), ``two_launch`` as summaries+mixing followed by the readout.
@@ -150,6 +153,12 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)
     d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
+    rms_w = None
+    if out_rms_weight is not None:
+        rms_w = out_rms_weight.detach().to(device=q.device, dtype=torch.float32).contiguous()
+        if rms_w.numel() != D:
+            raise ValueError(f"out_rms_weight must have {D} elements")
+    d.out_rms_weight, d.out_rms_eps = (rms_w.data_ptr() if rms_w is not None else None), float(out_rms_eps)
     stream = torch.cuda.current_stream(q.device)
     if single:
         ws = _persistent_ws(q.device, nbytes, stream.cuda_stream)
@@ -162,7 +171,7 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         with torch.cuda.device(q.device):
             _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
     # keep the operands alive until the stream has consumed them
-    for t in (q5, k5, v5, qr5, kr5, mix2) + (() if single else (ws,)):
+    for t in (q5, k5, v5, qr5, kr5, mix2, rms_w) + (() if single else (ws,)):
         if t is not None:
             t.record_stream(stream)
     res = o5 if out is None else out

@@ -168,6 +168,21 @@ def test_blockmix_full_size_configs(name, B, H, M, w, D, normalize, rope):
         _check(ref[0], out[b, h], torch.bfloat16)
 
 
+@pytest.mark.parametrize("B,H,M,w,D,normalize,rope", [(1, 2, 6, 210, 128, False, True), (2, 3, 8, 256, 64, True, False)])
+def test_blockmix_fused_output_rmsnorm(B, H, M, w, D, normalize, rope):
+    """Fused per-(token, head) RMSNorm of the output (MHLA_Video_Uni's g_norm, mhla_utils.py:360-362 with WanRMSNorm
+    wan/model.py:181-196) against the oracle followed by the same normalisation in fp32."""
+    q, k, v, qr, kr = _inputs(B, H, M, w, D, torch.bfloat16, seed=21, rope=rope)
+    g = torch.Generator().manual_seed(22)
+    W = torch.rand(M, M, generator=g) / M
+    wgt = torch.rand(D, generator=g) + 0.5
+    eps = 1e-5
+    out = _run(q, k, v, W, qr, kr, normalize=normalize, out_rms_weight=wgt.cuda(), out_rms_eps=eps)
+    ref = oracle.blockmix_fwd(q, k, v, W, normalize=normalize, q_rope=qr, k_rope=kr)
+    ref = ref * torch.rsqrt(ref.pow(2).mean(dim=-1, keepdim=True) + eps) * wgt
+    _check(ref, out, torch.bfloat16)
+
+
 def test_host_pipeline_matches_device_call():
     """mhla_host (pinned host tensors, copies and kernels pipelined over ranges of (b,h) units) is bit-identical to one
     device call on the whole batch - the units are independent."""
