@@ -682,12 +682,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         }
         const bool can2 = g2 >= 0 && (!dep2 || ready1_g == g2) && w_ok;
         const bool can3 = g3 >= 0 && (!dep3 || ready2_g == g3);
-        const bool can1 = cur1 >= 0 && (p.mode != 0 || p.policy == 1 || g3 < 0 || (int)(cur1 / p.M) < g3 + p.window);
+        const bool can1 = cur1 >= 0 && (p.mode != 0 || p.policy >= 1 || g3 < 0 || (int)(cur1 / p.M) < g3 + p.window);
         // Items alternate between the two epilogue warpgroups (FIFO index parity) and a P1 epilogue (normaliser) costs
         // about twice a P3 epilogue: when both kinds are available, give the heavier one to the less loaded warpgroup
         // instead of letting a strict P1/P3 alternation pile every P1 item onto the same warpgroup.
         int pick = 0;
-        if (can2) pick = 2;
+        if (can1 && p.policy == 2) pick = 1;          // policy 2: phase by phase (all summaries, then mixing, then readout)
+        else if (can2) pick = 2;
         else if (can1 && p.policy == 1) pick = 1;
         else if (can3 && can1) pick = (wg_load[pub & 1] <= wg_load[(pub & 1) ^ 1]) ? 1 : 3;
         else if (can3) pick = 3;
