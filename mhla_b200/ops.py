@@ -111,6 +111,17 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     for name, t in (("k", k5), ("v", v5), ("q_rope", qr5), ("k_rope", kr5)):
         if t is not None and tuple(t.shape) != (B, H, M, w, D):
             raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {(B, H, M, w, D)}")
+    D_in = D
+    if D not in (64, 128) and D < 128:
+        # head dims between the kernel's two widths (DiT-XL: 1152 / 16 = 72) run zero-padded: padded channels add exact
+        # zeros to K^T V, to the k-sums and to Q.S~, so the result is unchanged; the output is sliced back
+        if out is not None:
+            raise ValueError("out= is only supported for head dims 64 and 128")
+        D = 64 if D < 64 else 128
+        padc = lambda t: None if t is None else torch.nn.functional.pad(t, (0, D - D_in))  # noqa: E731
+        q5, k5, v5, qr5, kr5 = padc(q5), padc(k5), padc(v5), padc(qr5), padc(kr5)
+        if out_rms_weight is not None:
+            raise ValueError("out_rms_weight needs a head dim of 64 or 128 (the RMS would include the padding)")
     mix2 = mix.reshape(mix.shape[0], mix.shape[1]) if mix.dim() != 2 else mix
     if tuple(mix2.shape) != (M, M):
         raise ValueError(f"mix must be [{M}, {M}], got {tuple(mix.shape)}")
@@ -176,6 +187,8 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
             t.record_stream(stream)
     res = o5 if out is None else out
     if out is None:
+        if D_in != D:
+            res = res[..., :D_in]
         if squeeze:
             res = res.squeeze(1)
         if in_dtype != cdtype:

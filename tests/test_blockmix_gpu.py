@@ -183,6 +183,16 @@ def test_blockmix_fused_output_rmsnorm(B, H, M, w, D, normalize, rope):
     _check(ref, out, torch.bfloat16)
 
 
+def test_blockmix_padded_head_dim():
+    """DiT-XL heads (1152 / 16 = 72 channels, mhla_dit/models.py:478-549) run zero-padded to 128 in the shim."""
+    B, H, M, w, D = 1, 2, 16, 16, 72
+    q, k, v, _, _ = _inputs(B, H, M, w, D, torch.bfloat16, seed=31)
+    W = oracle.block_distance_matrix((4, 4), "linear")
+    out = _run(q, k, v, W)
+    assert out.shape[-1] == D
+    _check(oracle.blockmix_fwd(q, k, v, W), out, torch.bfloat16)
+
+
 def test_host_pipeline_matches_device_call():
     """mhla_host (pinned host tensors, copies and kernels pipelined over ranges of (b,h) units) is bit-identical to one
     device call on the whole batch - the units are independent."""
@@ -199,8 +209,9 @@ def test_host_pipeline_matches_device_call():
 
 def test_errors_are_loud():
     import mhla_b200
-    q = torch.zeros(1, 1, 2, 16, 32, dtype=torch.bfloat16, device="cuda")
+    q = torch.zeros(1, 1, 2, 16, 160, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(Exception):
-        mhla_b200.mhla(q, q, q, torch.eye(2, device="cuda"))          # D = 32 outside the envelope
+        mhla_b200.mhla(q, q, q, torch.eye(2, device="cuda"))          # D = 160 outside the envelope (D <= 128)
+    q = torch.zeros(1, 1, 2, 16, 32, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError):
         mhla_b200.mhla(q.cpu(), q.cpu(), q.cpu(), torch.eye(2))       # CPU tensors: no fallback
