@@ -525,7 +525,12 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
   mhla::prep_mix_kernel<<<8, 256, 0, stream>>>(d->mm, (long long)d->mm_ld, reinterpret_cast<uint16_t*>(ws + pl.off_W),
                                                pl.ns, pl.Mp, pl.n, 1, d->scale, d->dtype == MHLA_FP16, P.counters, 2 * pl.G);
   ++launches;
-  const int unfused = (d->flags & MHLA_FLAG_UNFUSED) ? 1 : 0;
+  // Measured on B200 (tools/causal_modes.py): with >= 512 chunks in flight the three phase-by-phase launches beat the
+  // statically scheduled single kernel (97 vs 105 us at B=8,H=4,T=2048,K=128,V=256; 101 vs 146 us at H=16,K=V=64), below
+  // that the single kernel wins (68 vs 80 us at B=2).  MHLA_FLAG_UNFUSED / MHLA_FLAG_FUSED force either.
+  int unfused = (long long)pl.G * pl.n >= 512 ? 1 : 0;
+  if (d->flags & MHLA_FLAG_UNFUSED) unfused = 1;
+  if (d->flags & MHLA_FLAG_FUSED) unfused = 0;
   rc = MHLA_ERR_UNSUPPORTED_SHAPE;
 #define MHLA_CAUSAL_CASE(KK, VV) \
   if (d->K == KK && d->V == VV) rc = mhla::causal_launch<KK, VV>(P, pl, unfused, g_num_sms, stream, &launches);

@@ -262,7 +262,7 @@ def _t4(t: torch.Tensor) -> _capi.Tensor4:
 
 
 def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
-                unfused: bool = False) -> torch.Tensor:
+                unfused: Optional[bool] = None) -> torch.Tensor:
     """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype.
 
     T is zero-padded to a multiple of the chunk exactly as the reference does (naive.py:46-51); the pad is a host-side
@@ -290,7 +290,8 @@ def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
         raise IndexError(f"mixing matrix is {Lm}x{Lm} but T={T_in} needs {n} chunks of {chunk_size}")
     d = _capi.CausalDesc()
     d.B, d.T, d.H, d.K, d.V = B, T, H, K, V
-    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], (_capi.FLAG_UNFUSED if unfused else 0)
+    # unfused: None = let the library choose (three launches for large batches), True / False force either structure
+    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], (0 if unfused is None else (_capi.FLAG_UNFUSED if unfused else _capi.FLAG_FUSED))
     d.scale = float(K ** -0.5 if scale is None else scale)
     d.q, d.k, d.v, d.out = _t4(q4), _t4(k4), _t4(v4), _t4(o4)
     d.mm, d.mm_ld, d.L = mm.data_ptr(), mm.stride(0), Lm
