@@ -61,7 +61,14 @@ _WS_CACHE: "dict[tuple, torch.Tensor]" = {}
 _WS_CACHE_MAX = 4
 
 
-_DESC_CACHE: "dict[tuple, tuple]" = {}
+class _Local(__import__("threading").local):
+    """Per-thread descriptor cache: a cached ctypes descriptor is mutated (pointers) on every call."""
+
+    def __init__(self):
+        self.desc = {}
+
+
+_TLS = _Local()
 
 
 def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int) -> torch.Tensor:
@@ -146,7 +153,8 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     L = _capi.lib()
     # the descriptor (shape, flags, workspace size) is cached per call signature; only pointers and strides change
     sig = (B, H, M, w, D, cdtype, flags, float(eps))
-    ent = _DESC_CACHE.get(sig)
+    cache = _TLS.desc
+    ent = cache.get(sig)
     if ent is None:
         d = _capi.BlockmixDesc()
         d.B, d.H, d.M, d.w, d.D = B, H, M, w, D
@@ -157,9 +165,9 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         if nbytes == 0:
             raise _capi.MhlaError(
                 f"unsupported blockmix shape B={B} H={H} M={M} w={w} D={D} (need D in {{64,128}}, w<=256)")
-        if len(_DESC_CACHE) > 64:
-            _DESC_CACHE.clear()
-        ent = _DESC_CACHE[sig] = (d, nbytes)
+        if len(cache) > 64:
+            cache.clear()
+        ent = cache[sig] = (d, nbytes)
     d, nbytes = ent
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)

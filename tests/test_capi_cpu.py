@@ -60,6 +60,16 @@ def test_blockmix_workspace_planning():
     assert L.mhla_blockmix_workspace_bytes(C.byref(_desc(dtype=7))) == 0
 
 
+def test_small_block_counts_are_packed_into_one_mixing_tile():
+    """Planner: with M <= 64 blocks per group, `pack` consecutive (b,h) groups (a divisor of B*H, pack * M <= 128) are
+    scheduled as one group with a block-diagonal mixing matrix; layout[7] is the padded size of that matrix."""
+    L = _capi.lib()
+    lay = (C.c_size_t * 8)()
+    for (B, H, M, want) in [(64, 6, 16, 128), (2, 16, 128, 128), (1, 5, 16, 80), (1, 1, 16, 16), (2, 12, 150, 152), (8, 4, 32, 128)]:
+        assert L.mhla_blockmix_workspace_layout(C.byref(_desc(B=B, H=H, M=M)), C.byref(lay)) == 0
+        assert int(lay[7]) == want, (B, H, M, int(lay[7]))
+
+
 def test_invalid_arguments_are_rejected_before_any_cuda_call():
     L = _capi.lib()
     d = _desc()
