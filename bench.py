@@ -3,13 +3,16 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W]            # our CUDA path (one JSON line on rank 0)
     python bench.py --impl reference [...]                          # reference CPU path (oracle port) on host cores
-    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # N>1: one rank per GPU, (b,h)-units sharded
+    python bench.py --impl reference-gpu [--sweep]                  # context arm: the reference's PyTorch core on the GPU
+                                                                    # (eager + torch.compile), fla linear attention, FlashAttention
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N    # N>1: one rank per GPU, (b,h) units sharded
 
 A "step" is one pass of the operator over one batch of synthetic block-major [B, H, M, w, D] tensors
-(w = 256, M = N / 256, W = BlockDistanceConv3D((M,1,1), "linear")), normaliser ON (DiT semantics): ONE launch of the fused
-persistent kernel per step (`--three-launch` / `--two-launch` time the multi-launch variants of the same kernel).  Multi-GPU is
-weak scaling over independent (b,h) units: every rank processes a full B=2,H=16 batch (global batch 2N), no
-data-path collective (`--gather` adds one NCCL all-gather of the outputs for the consumers that need all heads).
+(w = 256, M = N / 256, W = BlockDistanceConv3D((M,1,1), "linear")), normaliser ON (DiT semantics): ONE launch of the
+fused persistent kernel per step and rank.  Multi-GPU is STRONG scaling of exactly that batch: the 32 independent
+(b,h) units are partitioned contiguously over the ranks (32/16/8/4 units per GPU, `mhla_b200.sharded.mhla_sharded`),
+no data-path collective; the same run also times the variant with ONE NCCL all-gather of the outputs
+(`all_gather_into_tensor`, for consumers that need every head on every rank) and reports it as `with_gather`.
 """
 from __future__ import annotations
 
@@ -26,7 +29,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 B, H, N, D, WBLK = 2, 16, 32768, 64, 256
+UNITS = B * H
 METRIC = "MHLA fwd tokens/sec at seq_len 32768 (B=2,H=16,D=64)"
+L2_BYTES = 126e6
 
 
 def measured_peaks():
@@ -39,20 +44,26 @@ def measured_peaks():
 
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    try:
-        with open(path) as f:
-            return float(json.load(f)["dram_bytes_per_launch"])
-    except Exception:
-        return None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                return float(json.load(f)["dram_bytes_per_launch"]), name
+        except Exception:
+            continue
+    return None, None
 
 
-def make_inputs(device, seed, b=B, h=H, n=N, d=D, w=WBLK, pin=False):
+def make_units(lo, hi, n=N, d=D, w=WBLK, pin=False, salt=0):
+    """(b,h) units [lo, hi) of the synthetic workload, [units, M, w, D] bf16; unit u always comes from seed 1000+u, so a
+    sharded run works on exactly the tensors of the single-GPU run."""
     m = n // w
-    g = torch.Generator().manual_seed(seed)
-    q = (torch.relu(torch.randn(b, h, m, w, d, generator=g)) + 1e-6).to(torch.bfloat16)
-    k = (torch.relu(torch.randn(b, h, m, w, d, generator=g)) + 1e-6).to(torch.bfloat16)
-    v = torch.randn(b, h, m, w, d, generator=g).to(torch.bfloat16)
+    qs, ks, vs = [], [], []
+    for u in range(lo, hi):
+        g = torch.Generator().manual_seed(1000 + u + 100000 * salt)
+        qs.append((torch.relu(torch.randn(m, w, d, generator=g)) + 1e-6).to(torch.bfloat16))
+        ks.append((torch.relu(torch.randn(m, w, d, generator=g)) + 1e-6).to(torch.bfloat16))
+        vs.append(torch.randn(m, w, d, generator=g).to(torch.bfloat16))
+    q, k, v = torch.stack(qs), torch.stack(ks), torch.stack(vs)
     if pin:
         q, k, v = q.pin_memory(), k.pin_memory(), v.pin_memory()
     return q, k, v
@@ -100,12 +111,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def cpu_oracle_leg(steps, warmup, units, threads):
-    """Reference CPU path (oracle port of the reference's PyTorch-eager code) on `units` (b,h) units of the workload."""
+# ---------------------------------------------------------------------------------------------------- reference (CPU)
+def cpu_oracle_leg(steps, warmup, threads, n=N):
+    """Reference CPU path (oracle port of the reference's PyTorch-eager code) on the WHOLE workload: all 32 (b,h) units."""
     import oracle
     torch.set_num_threads(threads)
-    m = N // WBLK
-    q, k, v = make_inputs("cpu", 0, b=1, h=units)
+    m = n // WBLK
+    q, k, v = make_units(0, UNITS, n=n)
     q, k, v = q.float(), k.float(), v.float()
     W = oracle.block_distance_matrix((m, 1, 1), "linear")
     for _ in range(warmup):
@@ -114,44 +126,141 @@ def cpu_oracle_leg(steps, warmup, units, threads):
     for _ in range(steps):
         oracle.blockmix_fwd(q, k, v, W, normalize=True)
     dt = (time.perf_counter() - t0) / steps
-    # tokens are counted per full-width (H=16) batch element: `units` units = units/H of a sequence of N tokens
-    tok_s = (units / H) * N / dt
-    return tok_s, dt
+    return B * n / dt, dt
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    units = 2
-    steps = max(1, min(args.steps, 5))
-    warm = max(1, min(args.warmup, 1))
-    tok_s, dt = cpu_oracle_leg(steps, warm, units, threads)
-    sample = f"{units} of {B * H} (b,h) units of the headline workload per step (cost is linear in units), fp32, torch-CPU eager"
+    steps, warm = max(1, args.steps), max(1, args.warmup)
+    tok_s, dt = cpu_oracle_leg(steps, warm, threads)
+    sample = (f"the whole workload: all {UNITS} (b,h) units per step, fp32, torch-CPU eager restatement of "
+              "mhla_dit/mhla/mhla.py:262-268 (oracle port; the reference is Python and cannot travel to the GPU box)")
     line = {
         "impl": "reference", "metric": METRIC, "value": tok_s, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"blockmix A: B={B} H={H} N={N} D={D} w={WBLK} M={N // WBLK} normalize=1", "sample": sample},
+        "config": {"workload": f"blockmix A (mhla_dit core): B={B} H={H} N={N} D={D} w={WBLK} M={N // WBLK} normalize=1",
+                   "sample": sample},
         "cpu_baseline": {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": tok_s, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------- reference (GPU)
+def _timed(fn, reps, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3   # us
+
+
+def run_reference_gpu(args):
+    """Context arm (NOT the driver's reference arm): what the reference's own GPU path costs on this B200.
+    (i)  the reference core mhla_dit/mhla/mhla.py:262-268 - two batched matmuls, a bias-free 1x1 nn.Conv2d over the
+         block axis (twice), a divide - restated in torch around a real nn.Conv2d, eager and under torch.compile, in the
+         two precisions the reference trains in (fp32 with TF32 as mhla_dit/train.py:12-13 sets; bf16 autocast);
+    (ii) fla.ops.linear_attn.chunk_linear_attn (pip fla, Triton; plain causal linear attention, not MHLA) and
+    (iii) flash_attn_func at the same B, H, N, D, as context rows.  Ours is timed beside them."""
+    import mhla_b200
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    ns = [1024, 2048, 4096, 8192, 16384, 32768, 65536, 131072] if args.sweep else [N]
+    rows = []
+
+    def core(q, kt, v, conv, eps):
+        kv = conv(torch.matmul(kt, v))                                   # :262-263
+        normalizer = conv(torch.matmul(q, kt.sum(dim=-1, keepdim=True))) + eps   # :265-266
+        return torch.matmul(q, kv) / normalizer                          # :268
+
+    compiled = None
+    try:
+        compiled = torch.compile(core)
+    except Exception as e:   # noqa: BLE001
+        print(f"torch.compile unavailable: {e}", file=sys.stderr)
+    for n in ns:
+        m = n // WBLK
+        row = {"N": n, "M": m, "w": WBLK, "B": B, "H": H, "D": D}
+        g = torch.Generator(device=dev).manual_seed(0)
+        q = torch.relu(torch.randn(UNITS, m, WBLK, D, generator=g, device=dev)) + 1e-6
+        k = torch.relu(torch.randn(UNITS, m, WBLK, D, generator=g, device=dev)) + 1e-6
+        v = torch.randn(UNITS, m, WBLK, D, generator=g, device=dev)
+        Wm = mhla_b200.block_distance_matrix((m, 1, 1), "linear").to(dev) if m > 1 else torch.ones(1, 1, device=dev)
+        conv = torch.nn.Conv2d(m, m, 1, bias=False).to(dev)
+        conv.weight.data = Wm.view(m, m, 1, 1).clone()
+        reps = 20 if n <= 32768 else 5
+        qb, kb, vb = q.bfloat16(), k.bfloat16(), v.bfloat16()
+        out = torch.empty_like(qb)
+        with torch.no_grad():
+            row["ours_us"] = _timed(lambda: mhla_b200.mhla(qb, kb, vb, Wm, normalize=True, out=out), reps)
+            kt = k.transpose(-2, -1).contiguous()        # the reference materialises k^T in _process_qkv_impl (:236)
+            row["ref_eager_tf32_us"] = _timed(lambda: core(q, kt, v, conv, 1e-6), reps)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                row["ref_eager_bf16_autocast_us"] = _timed(lambda: core(q, kt, v, conv, 1e-6), reps)
+            if compiled is not None:
+                try:
+                    row["ref_compiled_tf32_us"] = _timed(lambda: compiled(q, kt, v, conv, 1e-6), reps)
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        row["ref_compiled_bf16_autocast_us"] = _timed(lambda: compiled(q, kt, v, conv, 1e-6), reps)
+                except Exception as e:   # noqa: BLE001
+                    row["ref_compiled_error"] = repr(e)[:200]
+                    compiled = None
+            del kt
+            # context rows at the same B, H, N, D (token-major [B, N, H, D])
+            qt = qb.view(B, H, n, D).transpose(1, 2).contiguous()
+            ktok = kb.view(B, H, n, D).transpose(1, 2).contiguous()
+            vt = vb.view(B, H, n, D).transpose(1, 2).contiguous()
+            try:
+                from fla.ops.linear_attn import chunk_linear_attn
+                row["fla_chunk_linear_attn_us"] = _timed(lambda: chunk_linear_attn(qt, ktok, vt, normalize=False), reps)
+            except Exception as e:   # noqa: BLE001
+                row["fla_error"] = repr(e)[:200]
+            try:
+                from flash_attn import flash_attn_func
+                row["flash_attn_us"] = _timed(lambda: flash_attn_func(qt, ktok, vt, causal=False), 3 if n > 32768 else 5, warm=1)
+            except Exception as e:   # noqa: BLE001
+                row["flash_attn_error"] = repr(e)[:200]
+        best_ref = min(v_ for k_, v_ in row.items() if k_.startswith("ref_") and k_.endswith("_us"))
+        row["speedup_vs_best_reference"] = best_ref / row["ours_us"]
+        row["ours_tokens_per_s"] = B * n / (row["ours_us"] * 1e-6)
+        rows.append(row)
+        print(json.dumps(row), file=sys.stderr)
+        del q, k, v, qb, kb, vb, out, qt, ktok, vt
+        torch.cuda.empty_cache()
+    head = next(r for r in rows if r["N"] == N) if any(r["N"] == N for r in rows) else rows[-1]
+    line = {"impl": "reference-gpu", "metric": METRIC, "unit": "us per forward (lower is better)", "n_gpus": 1,
+            "config": {"workload": f"B={B} H={H} D={D} w={WBLK}, N swept" if args.sweep else f"B={B} H={H} N={N} D={D} w={WBLK}"},
+            "headline": head, "rows": rows}
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, "r02_comparators.json"), "w") as f:
+            json.dump(line, f, indent=1)
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------- ours
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--gather", action="store_true", help="add one NCCL all-gather of the outputs per step (N>1)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-gpu"])
+    ap.add_argument("--sweep", action="store_true", help="reference-gpu: sweep N = 1k .. 128k")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the extra timed loop with the all-gather of the outputs")
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
-    ap.add_argument("--two-launch", action="store_true", help="summaries+mixing kernel followed by the readout kernel")
-    ap.add_argument("--fused", action="store_true", help="(default path; kept for old command lines)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -160,8 +269,13 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
+    if args.impl == "reference-gpu":
+        if rank == 0:
+            run_reference_gpu(args)
+        return
 
     import mhla_b200
+    from mhla_b200.sharded import mhla_sharded, unit_range
     import oracle  # checker / cpu_baseline only
 
     torch.cuda.set_device(local_rank)
@@ -171,60 +285,74 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     normalize = not args.no_normalize
-    path_kw = {"three_launch": True} if args.three_launch else ({"two_launch": True} if args.two_launch else {})
+    path_kw = {"three_launch": True} if args.three_launch else {}
     warm = max(args.warmup, 3)
     M = N // WBLK
+    lo, hi = unit_range(UNITS, world, rank)
+    nloc = hi - lo
 
-    hq, hk, hv = make_inputs("cpu", 100 + rank, pin=True)
-    q, k, v = hq.to(dev), hk.to(dev), hv.to(dev)
-    W = oracle.block_distance_matrix((M, 1, 1), "linear").to(dev)
-    out = torch.empty_like(q)
-    gathered = torch.empty((world,) + tuple(out.shape), dtype=out.dtype, device=dev) if (args.gather and world > 1) else None
+    # Rotating input sets keep the per-rank working set above L2 (126 MB): one set is 4 * nloc * N * D * 2 bytes.
+    set_bytes = 4 * nloc * N * D * 2
+    nsets = max(1, -(-int(3 * L2_BYTES) // set_bytes)) if set_bytes < 3 * L2_BYTES else 1
+    hq, hk, hv = make_units(lo, hi, pin=True)
+    sets = [(hq.to(dev), hk.to(dev), hv.to(dev), torch.empty((nloc, M, WBLK, D), dtype=torch.bfloat16, device=dev))]
+    for s_ in range(1, nsets):
+        g = torch.Generator(device=dev).manual_seed(7 + s_)
+        mk = lambda relu: ((torch.relu(torch.randn(nloc, M, WBLK, D, generator=g, device=dev)) + 1e-6) if relu  # noqa: E731
+                           else torch.randn(nloc, M, WBLK, D, generator=g, device=dev)).bfloat16()
+        sets.append((mk(True), mk(True), mk(False), torch.empty((nloc, M, WBLK, D), dtype=torch.bfloat16, device=dev)))
+    W = mhla_b200.block_distance_matrix((M, 1, 1), "linear").to(dev)
+    gathered = torch.empty((UNITS, M, WBLK, D), dtype=torch.bfloat16, device=dev) if world > 1 else None
+    it = [0]
 
-    def step():
-        mhla_b200.mhla(q, k, v, W, normalize=normalize, out=out, **path_kw)
-        if gathered is not None:
+    def step(gather=False):
+        q, k, v, out = sets[it[0] % nsets]
+        it[0] += 1
+        mhla_sharded(q, k, v, W, inputs="local", total_units=UNITS, gather=False, normalize=normalize, out=out, **path_kw)
+        if gather:
             dist.all_gather_into_tensor(gathered, out)
 
     # quick self-check of one (b,h) unit against the oracle before timing anything
     step()
     torch.cuda.synchronize()
-    ref = oracle.blockmix_fwd(hq[0, 0].float(), hk[0, 0].float(), hv[0, 0].float(), W.cpu(), normalize=normalize)
-    err = oracle.err_ratio(ref, out[0, 0].float().cpu())
+    ref = oracle.blockmix_fwd(hq[0][None].float(), hk[0][None].float(), hv[0][None].float(), W.cpu(), normalize=normalize)
+    err = oracle.err_ratio(ref[0], sets[0][3][0].float().cpu())
     if not err < 5e-3:
         raise SystemExit(f"bench self-check failed: err_ratio {err}")
+    it[0] = 0
 
-    for _ in range(warm):
-        step()
+    def timed_loop(gather):
+        for _ in range(warm):
+            step(gather)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            step(gather)
+        e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        return e0.elapsed_time(e1)
+
     sampler = ClockSampler(local_rank)
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    if dist is not None:
-        dist.barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = timed_loop(False)
     sampler.stop_flag = True
     launches_per_step = mhla_b200.last_launch_count()
+    ms_gather = timed_loop(True) if (world > 1 and not args.no_gather) else None
 
     # ---- end to end through the public API with HOST buffers (pinned H2D of q,k,v and D2H of the output per step)
-    hout = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    hout = torch.empty((nloc, M, WBLK, D), dtype=torch.bfloat16).pin_memory()
+    h5 = lambda t: t.view(nloc, 1, M, WBLK, D)   # noqa: E731
 
     def e2e_step():
         # the public host-tensor entry point: pinned H2D of q,k,v, the kernel and the D2H of the output, pipelined over
         # ranges of (b,h) units on three streams (mhla_b200.ops.mhla_host)
-        if path_kw:
-            dq, dk, dv = hq.to(dev, non_blocking=True), hk.to(dev, non_blocking=True), hv.to(dev, non_blocking=True)
-            hout.copy_(mhla_b200.mhla(dq, dk, dv, W, normalize=normalize, **path_kw), non_blocking=True)
-        else:
-            mhla_b200.mhla_host(hq, hk, hv, W, out=hout, normalize=normalize)
+        mhla_b200.mhla_host(h5(hq), h5(hk), h5(hv), W, out=h5(hout), normalize=normalize, chunks=min(8, nloc))
 
     e2e_step()
     torch.cuda.synchronize()
@@ -237,47 +365,58 @@ def main():
     f1.record()
     torch.cuda.synchronize()
     ms_e2e = f0.elapsed_time(f1)
+    e2e_ok = bool(torch.equal(hout, sets[0][3].cpu())) if nsets == 1 else None
 
     if dist is not None:
-        t = torch.tensor([ms_total, ms_e2e], device=dev)
+        t = torch.tensor([ms_total, ms_e2e, ms_gather or 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+        ms_total, ms_e2e, mg = t.tolist()
+        ms_gather = mg if ms_gather is not None else None
     ms_step = ms_total / args.steps
-    tokens_per_step = world * B * N
+    tokens_per_step = B * N                       # strong scaling: the batch is fixed, the ranks share it
     value = tokens_per_step / (ms_step * 1e-3)
     e2e_value = tokens_per_step / (ms_e2e / args.e2e_steps * 1e-3)
-    in_bytes = 3 * B * H * N * D * 2
-    out_bytes = B * H * N * D * 2
+    unit_bytes = N * D * 2
+    in_bytes, out_bytes = 3 * nloc * unit_bytes, nloc * unit_bytes          # this rank's share
     peak, peak_src = measured_peaks()
-    achieved = (in_bytes + out_bytes) / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes / step time
+    alg_bytes = 4 * nloc * unit_bytes
+    achieved = alg_bytes / (ms_step * 1e-3) / 1e9      # per GPU: algorithmic bytes of its launch / step time
+    traffic, traffic_src = measured_traffic()
     line = {
         "metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
         "config": {
-            "workload": f"blockmix A (mhla_dit core): B={B} H={H} N={N} D={D} w={WBLK} M={M} normalize={int(normalize)} per GPU",
-            "parallelism": f"(b,h)-sharded x{world}, no collective" + (" + all-gather(out)" if gathered is not None else ""),
-            "l2": "inputs+outputs 537 MB per step > 126 MB L2 (no explicit flush)",
+            "workload": f"blockmix A (mhla_dit core): B={B} H={H} N={N} D={D} w={WBLK} M={M} normalize={int(normalize)} (whole job)",
+            "parallelism": (f"{UNITS} (b,h) units sharded over {world} rank(s), {nloc} per GPU, no data-path collective"
+                            + ("; with_gather adds one NCCL all_gather_into_tensor of the outputs behind the kernel" if ms_gather else "")),
+            "l2": (f"{nsets} rotating input/output set(s) of {set_bytes / 1e6:.0f} MB per rank: working set "
+                   f"{nsets * set_bytes / 1e6:.0f} MB > 126 MB L2 (no explicit flush)"),
         },
         "roofline": {
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": (measured_traffic() if (normalize and not path_kw) else None), "peak_source": peak_src,
-            "note": "algorithmic bytes = Q,K,V read + O write = 4*B*H*N*D*2 = 536.9 MB per launch; duration = CUDA-event "
-                    "time per step = one launch of blockmix_kernel<64> (the only kernel of a step); traffic = dram read + "
-                    "write bytes of that launch from the committed ncu --set full capture (profiles/r01_traffic.json)",
+            "traffic": (traffic if (normalize and not path_kw and world == 1) else None), "peak_source": peak_src,
+            "note": f"algorithmic bytes = Q,K,V read + O write = 4*units*N*D*2 = {alg_bytes / 1e6:.1f} MB per launch on this "
+                    "GPU; duration = CUDA-event time per step = one launch of blockmix_kernel<64> (the only kernel of a "
+                    f"step); traffic = dram read + write bytes of that launch from the committed ncu --set full capture "
+                    f"(profiles/{traffic_src})",
         },
-        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
-                "ms_per_step": ms_e2e / args.e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": in_bytes * world, "d2h_bytes_per_step": out_bytes * world,
+                "ms_per_step": ms_e2e / args.e2e_steps, "bit_identical_to_device_path": e2e_ok},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": sampler.summary(),
         "self_check_err_ratio": err,
     }
+    if ms_gather is not None:
+        mg = ms_gather / args.steps
+        line["with_gather"] = {"value": tokens_per_step / (mg * 1e-3), "unit": "tokens/s", "ms_per_step": mg,
+                               "all_gather_bytes": UNITS * unit_bytes}
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            tok_s, dt = cpu_oracle_leg(3, 1, 2, threads)
+            tok_s, dt = cpu_oracle_leg(3, 1, threads)
             line["cpu_baseline"] = {"value": tok_s, "unit": "tokens/s", "cores": threads, "kind": "port",
-                                    "sample": "2 of 32 (b,h) units per step, 3 steps, fp32 torch-CPU eager oracle"}
+                                    "sample": f"the whole workload (all {UNITS} (b,h) units) per step, 3 steps, fp32 torch-CPU eager oracle"}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

@@ -77,6 +77,31 @@ bool encode_map(CUtensorMap* out, const MapSpec& s) {
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (separate L2 sectors)
 
+// Tuning / debugging knobs of the blockmix kernel, read from the environment ONCE (first call).
+struct Knobs {
+  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, ws_hint = 1, q_keep = 0, trace_cta = 0, slots = 2;
+  bool no_pack = false, no_self_prep = false;
+};
+const Knobs& knobs() {
+  static Knobs k;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    auto geti = [](const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; };
+    k.run_ahead = geti("MHLA_RUNAHEAD", k.run_ahead);
+    if (k.run_ahead < 1) k.run_ahead = 1;
+    if (k.run_ahead > 16) k.run_ahead = 16;
+    k.mix_hi_only = geti("MHLA_MIX_HI_ONLY", 0);
+    k.o_hint = geti("MHLA_OHINT", 1);
+    k.ws_hint = geti("MHLA_WSHINT", 1);
+    k.q_keep = geti("MHLA_QKEEP", 0);
+    k.trace_cta = geti("MHLA_TRACE_CTA", 0);
+    k.slots = geti("MHLA_SLOTS", 2) == 1 ? 1 : 2;
+    k.no_pack = std::getenv("MHLA_NO_PACK") != nullptr;
+    k.no_self_prep = std::getenv("MHLA_NO_SELF_PREP") != nullptr;
+  });
+  return k;
+}
+
 // ------------------------------------------------------------------------------------------------ blockmix
 struct BlockmixPlan {
   int G, TW, nsub, wpad, ncols, Mp, n2_rows, n2_cols, n2_scols, kslabs, normalize, ropenorm;
@@ -103,7 +128,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   // mixing matrix is block-diagonal (pack copies of the caller's matrix).  Their rows are consecutive in the workspace,
   // so nothing else changes; pack must divide the number of groups.
   pl->pack = 1;
-  if (!std::getenv("MHLA_NO_PACK"))
+  if (!knobs().no_pack)
     for (int pk = 128 / d->M; pk >= 2; --pk)
       if (pl->G % pk == 0) { pl->pack = pk; break; }
   pl->Gs = pl->G / pl->pack;
@@ -221,15 +246,39 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->ncols = pl.ncols; P->wpad = pl.wpad;
   P->n2_rows = pl.n2_rows; P->n2_cols = pl.n2_cols; P->n2_scols = pl.n2_scols; P->kslabs = pl.kslabs;
   P->normalize = pl.normalize; P->ropenorm = pl.ropenorm; P->is_fp16 = d->dtype == MHLA_FP16;
-  P->mode = 0; P->window = 8; P->run_ahead = 2; P->cnt_stride = kCntStride;
+  P->mode = 0; P->run_ahead = 2; P->cnt_stride = kCntStride;
   P->eps = d->eps;
   (void)Wp;
   return MHLA_OK;
 }
 
-int g_num_sms = 0;
 unsigned long long* g_prof_buffer = nullptr;   // debug: per-CTA role counters (mhla_debug_set_profile_buffer)
-bool g_attr_set64 = false, g_attr_set128 = false;
+
+// Per-device state (SM count, dynamic shared-memory opt-in per kernel instantiation), guarded by g_cache_mu.
+constexpr int kMaxDevices = 64;
+struct DeviceState {
+  int sms = 0;          // 0: not queried yet; < 0: not an sm_100 device
+  bool attr64 = false, attr128 = false;
+};
+DeviceState g_dev[kMaxDevices];
+
+// resolves the current device; returns MHLA_OK and its state, or an error
+int device_state(DeviceState** out) {
+  int dev = 0;
+  if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return MHLA_ERR_CUDA;
+  if (dev < 0 || dev >= kMaxDevices) return MHLA_ERR_NO_DEVICE;
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  DeviceState& st = g_dev[dev];
+  if (st.sms == 0) {
+    int major = 0, sms = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    st.sms = (major == 10 && sms > 0) ? sms : -1;
+  }
+  if (st.sms < 0) return MHLA_ERR_NO_DEVICE;
+  *out = &st;
+  return MHLA_OK;
+}
 
 }  // namespace
 
@@ -280,15 +329,10 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (d->q_rope.ptr && (!t5_ok(d->q_rope) || !t5_ok(d->k_rope))) return MHLA_ERR_ALIGNMENT;
   if (d->mix_ld < d->M) return MHLA_ERR_INVALID_ARGUMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-
-  if (g_num_sms == 0) {
-    int dev = 0, major = 0, sms = 0;
-    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return MHLA_ERR_CUDA;
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (major != 10) return MHLA_ERR_NO_DEVICE;
-    g_num_sms = sms;
-  }
+  DeviceState* dst = nullptr;
+  rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  const int num_sms = dst->sms;
 
   mhla::BlockmixParams P;
   {
@@ -308,47 +352,31 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     }
   }
 
+  const Knobs& kn = knobs();
   P.prof = g_prof_buffer;
-  if (const char* e = std::getenv("MHLA_WINDOW")) P.window = std::atoi(e);       // tuning knobs of the fused kernel's
-  if (const char* e = std::getenv("MHLA_RUNAHEAD")) P.run_ahead = std::atoi(e);  // run-time scheduler
-  P.np2 = -1;
-  P.trace_cta = 0;
-  P.mix_hi_only = 0;
-  if (const char* e = std::getenv("MHLA_MIX_HI_ONLY")) P.mix_hi_only = std::atoi(e);
-  P.policy = 1;
-  P.o_hint = 1;
-  P.q_hint = 1;
-  if (const char* e = std::getenv("MHLA_QHINT")) P.q_hint = std::atoi(e);
-  if (const char* e = std::getenv("MHLA_OHINT")) P.o_hint = std::atoi(e);
-  if (const char* e = std::getenv("MHLA_POLICY")) P.policy = std::atoi(e);
-  P.pf_dist = 0;
-  if (const char* e = std::getenv("MHLA_PF")) P.pf_dist = std::atoi(e);
-  if (const char* e = std::getenv("MHLA_TRACE_CTA")) P.trace_cta = std::atoi(e);
-  if (const char* e = std::getenv("MHLA_NP2")) P.np2 = std::atoi(e);
-  if (P.window < 1) P.window = 1;
-  if (P.run_ahead < 1) P.run_ahead = 1;
-  if (P.run_ahead > 16) P.run_ahead = 16;
+  P.run_ahead = kn.run_ahead;
+  P.trace_cta = kn.trace_cta;
+  P.mix_hi_only = kn.mix_hi_only;
+  P.o_hint = kn.o_hint;
+  P.ws_hint = kn.ws_hint;
+  P.q_keep = kn.q_keep;
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
-  bool& attr = d->D == 64 ? g_attr_set64 : g_attr_set128;
-  if (!attr) {
-    if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
-                 "cudaFuncSetAttribute"))
-      return MHLA_ERR_CUDA;
-    attr = true;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    bool& attr = d->D == 64 ? dst->attr64 : dst->attr128;
+    if (!attr) {
+      if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
+                   "cudaFuncSetAttribute"))
+        return MHLA_ERR_CUDA;
+      attr = true;
+    }
   }
 
   uint8_t* ws = static_cast<uint8_t*>(d->workspace);
   int launches = 0;
   const bool dbg_phase = (d->flags & (MHLA_FLAG_STOP_AFTER_P1 | MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2)) != 0;
-  // Known issue (round 1, tools/stress_wan.py): at Wan size (B*H = 24, M = 150, w = 210, D = 128) with BOTH the roped
-  // numerator and the normaliser, the fused kernel has hit a rare launch failure (about 1 call in several hundred; a
-  // bounded-spin trap, i.e. a stall somewhere in the in-kernel dependency machinery).  Until it is understood that
-  // combination takes the three phase-by-phase launches, which have no in-kernel dependencies; MHLA_FLAG_FUSED still
-  // forces the single kernel.  The shipped Wan configuration (normaliser off) is not affected.
-  const bool rope_norm = pl.ropenorm != 0;
-  const bool single = (d->flags & MHLA_FLAG_FUSED) ||
-                      !(dbg_phase || rope_norm || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
-  P.self_prep = (single && (d->flags & MHLA_FLAG_WS_PERSISTENT) && !std::getenv("MHLA_NO_SELF_PREP")) ? 1 : 0;
+  const bool single = (d->flags & MHLA_FLAG_FUSED) || !(dbg_phase || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
+  P.self_prep = (single && (d->flags & MHLA_FLAG_WS_PERSISTENT) && !kn.no_self_prep) ? 1 : 0;
   if (!P.self_prep) {
     mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
                                                        reinterpret_cast<uint16_t*>(ws + pl.off_W), pl.Ms, pl.Mp, d->M,
@@ -372,45 +400,31 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
     return cuda_ok(cudaLaunchKernelEx(&cfg, kern, P), "cudaLaunchKernelEx");
   };
   if (!single) {
+    // MHLA_FLAG_UNFUSED / the debugging flags: plain phase-by-phase launches of the same kernel, chained with PDL
     int last = (d->flags & MHLA_FLAG_STOP_AFTER_P1) ? 1 : ((d->flags & MHLA_FLAG_STOP_AFTER_P2) ? 2 : 3);
     int first = (d->flags & MHLA_FLAG_ONLY_P3) ? 3 : 1;
     if (d->flags & MHLA_FLAG_ONLY_P2) first = last = 2;
-    // MHLA_FLAG_TWO_LAUNCH: summaries + block mixing in one dynamically scheduled kernel (mode 4: the mixing of a group
-    // starts as soon as its summaries are complete), then the readout as a second launch that starts on the counters
-    // while the first grid drains (mode 5).  MHLA_FLAG_UNFUSED / the debugging flags: plain phase-by-phase launches.
-    const bool two_launch = first == 1 && last == 3 && (d->flags & MHLA_FLAG_TWO_LAUNCH) != 0;
-    P.reverse3 = two_launch ? 1 : 0;
-    if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     for (int mode = first; mode <= last; ++mode) {
-      if (two_launch && mode == 2) continue;
-      P.mode = (two_launch && mode == 1) ? 4 : ((two_launch && mode == 3) ? 5 : mode);
-      // P1 with D = 64 only stages 1 KB (n_loc) + 8 KB (S) per item: give the ring a sixth stage instead (a multiple
-      // of the 3 stages per item keeps the long-lived Q stage out of the K/V recycling path)
-      const bool small_staging = (P.mode == 1 && d->D == 64);
+      P.mode = mode;
+      // P1 with D = 64 only stages 8 KB (S) per item: give the ring a sixth stage instead (a multiple of the 3 stages
+      // per item keeps the long-lived Q stage out of the K/V recycling path)
+      const bool small_staging = (mode == 1 && d->D == 64);
       P.slot_bytes = small_staging ? 8192 : 16384;
       P.ring_stages = small_staging ? 6 : 5;
       P.slots_per_wg = 2;
-      if (P.mode == 4 && P.np2 < 0) P.np2 = 0;
-      const long long items = (long long)pl.Gs * (P.mode == 4 ? n1 + n2 : (mode == 1 ? n1 : (mode == 2 ? n2 : n3)));
-      if (P.mode != 4 && P.mode != 0) P.np2 = 0;
-      const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-      if (P.np2 > grid / 2) P.np2 = grid / 2;
+      const long long items = (long long)pl.Gs * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
+      const int grid = (int)(items < num_sms ? items : num_sms);
       if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
       ++launches;
     }
   } else {
     P.mode = 0;
-    P.reverse3 = 0;
-    if (const char* e = std::getenv("MHLA_REVERSE3")) P.reverse3 = std::atoi(e);
     P.slot_bytes = 16384;
-    P.slots_per_wg = 2;
-    if (const char* e = std::getenv("MHLA_SLOTS")) P.slots_per_wg = std::atoi(e) == 1 ? 1 : 2;
+    P.slots_per_wg = kn.slots;
     P.ring_stages = P.slots_per_wg == 1 ? 6 : 5;   // one staging slot per warpgroup buys a sixth ring stage
     const long long items = (long long)pl.Gs * (n1 + n2 + n3);
-    const int grid = (int)(items < g_num_sms ? items : g_num_sms);
-    // dedicated block-mixing CTAs: one per P2 tile of a group, when that leaves most of the grid for streaming
-    if (P.np2 < 0) P.np2 = 0;   // (dedicated mixing CTAs are a tuning option: MHLA_NP2)
-    if (P.np2 > grid / 2) P.np2 = grid / 2;
+    // 1 CTA per SM (224 KB of shared memory): the grid never exceeds what is co-resident on an otherwise idle device
+    const int grid = (int)(items < num_sms ? items : num_sms);
     if (!launch_pdl(grid)) return MHLA_ERR_CUDA;
     ++launches;
   }
@@ -422,6 +436,15 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
 /* Debug hook (not part of the stable ABI): device buffer of [#SMs][16] uint64 that receives per-CTA wait-cycle counters
  * of the blockmix kernel's warp roles; NULL switches the instrumentation off. */
 void mhla_debug_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
+
+/* Debug hook (not part of the stable ABI): host-mapped (pinned, zero-copy) buffer of 1 + 148*64 uint64 that receives a
+ * record from every wait that hits its time bound before the kernel traps; NULL switches it off.  Applies to the
+ * current device. */
+int mhla_debug_set_diag_buffer(void* host_mapped_ptr) {
+  unsigned long long* p = static_cast<unsigned long long*>(host_mapped_ptr);
+  if (!cuda_ok(cudaMemcpyToSymbol(mhla::g_mhla_diag, &p, sizeof p), "cudaMemcpyToSymbol(g_mhla_diag)")) return MHLA_ERR_CUDA;
+  return MHLA_OK;
+}
 
 int mhla_blockmix_workspace_init(const mhla_blockmix_desc* d, void* stream_) {
   BlockmixPlan pl;
@@ -451,14 +474,10 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
   }
   if (d->mm_ld < pl.n) return MHLA_ERR_INVALID_ARGUMENT;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  if (g_num_sms == 0) {
-    int dev = 0, major = 0, sms = 0;
-    if (!cuda_ok(cudaGetDevice(&dev), "cudaGetDevice")) return MHLA_ERR_CUDA;
-    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (major != 10) return MHLA_ERR_NO_DEVICE;
-    g_num_sms = sms;
-  }
+  DeviceState* dst = nullptr;
+  rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  const int num_sms = dst->sms;
 
   mhla::CausalParams P;
   {
@@ -540,7 +559,7 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
   if (d->flags & MHLA_FLAG_FUSED) unfused = 0;
   rc = MHLA_ERR_UNSUPPORTED_SHAPE;
 #define MHLA_CAUSAL_CASE(KK, VV) \
-  if (d->K == KK && d->V == VV) rc = mhla::causal_launch<KK, VV>(P, pl, unfused, g_num_sms, stream, &launches);
+  if (d->K == KK && d->V == VV) rc = mhla::causal_launch<KK, VV>(P, pl, unfused, num_sms, stream, &launches);
   MHLA_CAUSAL_CASE(64, 64)
   MHLA_CAUSAL_CASE(64, 128)
   MHLA_CAUSAL_CASE(128, 128)

@@ -9,10 +9,51 @@
 
 namespace mhla {
 
-// A wait that never completes would hang the GPU box; every spin is bounded and traps instead.
-#ifndef MHLA_SPIN_LIMIT
-#define MHLA_SPIN_LIMIT (1u << 26)
+// A wait that never completes would hang the GPU box: every spin is bounded in TIME (globaltimer) and, when the bound
+// expires, records who was waiting for what in a host-mapped diagnostics buffer (if the host installed one with
+// mhla_debug_set_diag_buffer), lingers long enough for the other stalled roles to record themselves too, and traps.
+#ifndef MHLA_STALL_NS
+#define MHLA_STALL_NS 8000000000ull   /* 8 s: far beyond any legitimate wait (a whole launch takes < 1 ms) */
 #endif
+
+__device__ unsigned long long* g_mhla_diag = nullptr;   // [1 + 148 * 64] uint64, host-mapped (zero-copy) memory
+
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// codes: 1 mbarrier (a = shared address, b = parity)   2 item stream (a = role, b = index)   3 scheduler throttle
+//        4 scheduler idle (a = claimed kinds, b = counter value)   5 signal warp (a = warpgroup, b = seen)   6 counter spin
+__device__ __noinline__ void report_stall(uint32_t code, uint32_t a, uint32_t b) {
+  unsigned long long* d = g_mhla_diag;
+  if (d != nullptr) {
+    // one record of 4 words per (block, warp): [code | thread << 32, a | b << 32, clock64, globaltimer]
+    unsigned long long* r = d + 1 + ((size_t)(blockIdx.x % 148) * 16 + (threadIdx.x >> 5)) * 4;
+    r[0] = (unsigned long long)code | ((unsigned long long)threadIdx.x << 32) | (1ull << 63);
+    r[1] = (unsigned long long)a | ((unsigned long long)b << 32);
+    r[2] = (unsigned long long)clock64();
+    r[3] = gtimer_ns();
+    d[0] = 0x4d484c41ull;   // "MHLA": at least one record is valid
+    __threadfence_system();
+  }
+  printf("mhla: stalled wait code %u (block %d thread %d a %u b %u)\n", code, blockIdx.x, threadIdx.x, a, b);
+  for (int i = 0; i < 4000; ++i) __nanosleep(100000);   // ~0.4 s: let the other stalled roles report as well
+  __trap();
+}
+
+struct SpinGuard {
+  uint32_t n = 0;
+  unsigned long long t0 = 0;
+  // true once the wait has lasted longer than MHLA_STALL_NS (the clock is only read every 16384 polls)
+  __device__ __forceinline__ bool expired() {
+    if ((++n & 0x3FFFu) != 0) return false;
+    const unsigned long long t = gtimer_ns();
+    if (t0 == 0) { t0 = t; return false; }
+    return t - t0 > MHLA_STALL_NS;
+  }
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -54,13 +95,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
+  SpinGuard guard;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > MHLA_SPIN_LIMIT) {
-      printf("mhla: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
-    }
+    if (guard.expired()) report_stall(1, smem_u32(bar), parity);
   }
 }
 
@@ -171,6 +208,13 @@ __device__ __forceinline__ void tma_store_5d_hint(const void* tmap, const void* 
   asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5, %6}], [%1], %7;" ::"l"(
                    reinterpret_cast<uint64_t>(tmap)),
                "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "l"(hint)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_3d_hint(const void* tmap, const void* smem, int c0, int c1, int c2,
+                                                  uint64_t hint) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4}], [%1], %5;" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "l"(hint)
                : "memory");
 }
 // 1-D bulk copy shared -> global (no tensor map); size multiple of 16, both addresses 16-byte aligned

@@ -71,8 +71,9 @@ class _Local(__import__("threading").local):
 _TLS = _Local()
 
 
-def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int) -> torch.Tensor:
-    key = (device.index, stream_handle, nbytes)
+def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int, sig: tuple) -> torch.Tensor:
+    # keyed by the full call signature: two shapes of equal total size lay the control block out differently
+    key = (device.index, stream_handle, nbytes) + tuple(sig)
     ws = _WS_CACHE.get(key)
     if ws is None:
         if len(_WS_CACHE) >= _WS_CACHE_MAX:
@@ -143,15 +144,10 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
 
     if unfused is not None:          # spelling used by the tests: unfused=True -> three launches
         three_launch = bool(unfused)
-    if qr5 is not None and normalize and not (two_launch or debug_flags or force_fused):
-        # known issue (tools/stress_wan.py): roped numerator + normaliser at Wan size has hit a rare
-        # launch failure in the fused kernel; that combination runs as three launches until it is understood
+    if two_launch or not fused:      # (the two-launch variant of round 1 is gone: it now means phase-by-phase launches)
         three_launch = True
-    flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else 0) |
-             (_capi.FLAG_TWO_LAUNCH if two_launch else 0) | int(debug_flags))
-    if not fused and not (three_launch or two_launch or debug_flags):
-        flags |= _capi.FLAG_TWO_LAUNCH
-    single = not (three_launch or two_launch or debug_flags or not fused)
+    flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else 0) | int(debug_flags))
+    single = not (three_launch or debug_flags)
     if single:
         flags |= _capi.FLAG_WS_PERSISTENT | (_capi.FLAG_FUSED if force_fused else 0)
     L = _capi.lib()
@@ -184,7 +180,7 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     d.out_rms_weight, d.out_rms_eps = (rms_w.data_ptr() if rms_w is not None else None), float(out_rms_eps)
     stream = torch.cuda.current_stream(q.device)
     if single:
-        ws = _persistent_ws(q.device, nbytes, stream.cuda_stream)
+        ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig)
     else:
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
     d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes

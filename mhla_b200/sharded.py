@@ -22,12 +22,15 @@ def unit_range(n_units: int, world: int, rank: int) -> Tuple[int, int]:
 
 
 def mhla_sharded(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mix: torch.Tensor, *, group=None,
-                 gather: bool = True, inputs: str = "full", compute: Optional[Callable] = None, **kw) -> torch.Tensor:
+                 gather: bool = True, inputs: str = "full", total_units: Optional[int] = None,
+                 compute: Optional[Callable] = None, **kw) -> torch.Tensor:
     """Block-mixed MHLA on (b,h)-sharded units.
 
     q, k, v : [G, M, w, D] with G = B*H flattened units (``inputs="full"``: every rank holds all G units and works on
               its own slice; ``inputs="local"``: the tensors already are this rank's slice, e.g. behind head-sharded
               projections).  Extra keyword tensors ``q_rope`` / ``k_rope`` follow the same convention.
+    total_units : ``inputs="local"`` only - the global number of units G when the caller knows it (skips the count
+              exchange, so the call enqueues the kernel and nothing else).
     gather  : all-gather the outputs so every rank returns the full [G, M, w, D]; otherwise return the local slice.
     compute : the single-GPU operator (defaults to ``mhla_b200.mhla_blockmix``; the CPU tests inject the oracle to
               exercise this host logic under gloo).
@@ -46,8 +49,10 @@ def mhla_sharded(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mix: torch.T
         rope = {n: t[lo:hi] for n, t in rope.items()}
     elif inputs == "local":
         ql, kl, vl = q, k, v
-        counts = torch.tensor([q.shape[0]], device=q.device)
-        if world > 1:
+        counts = torch.tensor([q.shape[0]], device=q.device) if total_units is None else None
+        if total_units is not None:
+            G = int(total_units)
+        elif world > 1:
             allc = [torch.zeros_like(counts) for _ in range(world)]
             dist.all_gather(allc, counts, group=group)
             G = int(sum(int(c) for c in allc))

@@ -55,10 +55,10 @@ def _run(q, k, v, W, qr=None, kr=None, normalize=True, eps=1e-6, **kw):
     (1, 2, 5, 100, 64, True, False, torch.float16),         # ragged w, fp16
     (1, 1, 1, 256, 64, True, False, torch.bfloat16),        # single block
 ])
-@pytest.mark.parametrize("path", ["fused", "three_launch", "two_launch"])
+@pytest.mark.parametrize("path", ["fused", "three_launch"])
 def test_blockmix_vs_oracle(B, H, M, w, D, normalize, rope, dtype, path):
-    """Every launch structure of the C ABI (the default single fused kernel, the three PDL-chained phase launches and
-    the two-launch variant) against the oracle."""
+    """Both launch structures of the C ABI (the default single fused kernel and the three PDL-chained phase launches)
+    against the oracle."""
     q, k, v, qr, kr = _inputs(B, H, M, w, D, dtype, rope=rope)
     g = torch.Generator().manual_seed(1)
     W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
@@ -73,10 +73,7 @@ def test_blockmix_vs_reference_golden(name):
     the kernel computes in bf16, so compare against the oracle on bf16-rounded inputs AND against the reference's fp32
     output with the rounding of the inputs added to the budget."""
     g = load_golden(name)
-    D = g["q"].shape[-1]
-    if D not in (64, 128):
-        pytest.skip("fixture head dim outside the kernel envelope (oracle-only fixture)")
-    bf = torch.bfloat16
+    bf = torch.bfloat16          # (D = 32 fixtures run zero-padded to 64 channels inside the shim)
     q, k, v = g["q"].to(bf), g["k"].to(bf), g["v"].to(bf)
     qr = g["q_rope"].to(bf) if "q_rope" in g else None
     kr = g["k_rope"].to(bf) if "k_rope" in g else None

@@ -47,7 +47,7 @@ def timed(fn):
 
 for normalize in ([False] if "--no-normalize" in sys.argv else [True, False]):
     res = {}
-    for name, kw in (("full", {}), ("two", {"two_launch": True}), ("three", {"three_launch": True}), ("P1", {"debug_flags": _capi.FLAG_STOP_AFTER_P1}),
+    for name, kw in (("full", {}), ("three", {"three_launch": True}), ("P1", {"debug_flags": _capi.FLAG_STOP_AFTER_P1}),
                      ("P2", {"debug_flags": _capi.FLAG_ONLY_P2}), ("P3", {"debug_flags": _capi.FLAG_ONLY_P3}),
                      ):
         try:

@@ -11,7 +11,7 @@ import mhla_b200  # noqa: E402
 from mhla_b200 import _capi  # noqa: E402
 
 normalize = "--no-normalize" not in sys.argv
-KW = dict(fused=True)
+KW = {}
 for m, f in (("--p1only", _capi.FLAG_STOP_AFTER_P1), ("--p2only", _capi.FLAG_ONLY_P2), ("--p3only", _capi.FLAG_ONLY_P3)):
     if m in sys.argv:
         KW = dict(debug_flags=f)
@@ -39,7 +39,7 @@ L.mhla_debug_set_profile_buffer(None)
 p = prof.cpu().double()
 names = ["prod.wait_empty", "prod.wait_dep", "prod.total", "mma.wait_full", "mma.wait_tempty", "epi.wait_tfull",
          "epi.wait_sfree", "epi.t_ld+pack", "epi.t_P1", "epi.t_P2", "epi.t_P3", "epi.items", "epi.t_tmem_ld",
-         "epi.t_copy", "gt", "epi.t_stage"]
+         "epi.t_flush", "gt", "epi.t_stage"]
 print(f"normalize={normalize}  step (events) = {e0.elapsed_time(e1) * 1e3:.1f} us")
 print("SM clock (GHz) from clock64/globaltimer over the producer lifetime: mean %.3f min %.3f max %.3f ; lifetime us mean %.1f" % ((p[:,2]/p[:,14]).mean(), (p[:,2]/p[:,14]).min(), (p[:,2]/p[:,14]).max(), p[:,14].mean()/1e3))
 tot = p[:, 2].mean()

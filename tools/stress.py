@@ -1,0 +1,89 @@
+"""Stress the fused blockmix kernel: repeat one call many times, check every result bit-for-bit against the first one
+(and the first one against the oracle), and - if a wait inside the kernel ever hits its time bound - decode the
+diagnostics the kernel wrote to host-mapped memory before it trapped.
+
+    python tools/stress.py <preset> <calls> [three_launch]
+presets: wan_norm (B*H=24, M=150, w=210, D=128, rope + normaliser), wan (shipped: no normaliser), headline, dit64
+"""
+import ctypes as C
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mhla_b200  # noqa: E402
+import oracle  # noqa: E402  (checker)
+from mhla_b200 import _capi  # noqa: E402
+
+PRESETS = {
+    "wan_norm": (2, 12, 150, 210, 128, True, True),
+    "wan": (1, 12, 150, 210, 128, False, True),
+    "headline": (2, 16, 128, 256, 64, True, False),
+    "dit64": (64, 6, 16, 16, 64, True, False),
+    "small_rope": (1, 3, 20, 210, 128, True, True),
+}
+CODES = {1: "mbarrier", 2: "item stream", 3: "scheduler throttle", 4: "scheduler idle", 5: "signal warp", 6: "counter spin"}
+
+
+def decode(diag):
+    if int(diag[0]) != 0x4D484C41:
+        print("no stall record in the diagnostics buffer")
+        return
+    recs = diag[1:].view(148, 16, 4)
+    for b in range(148):
+        for w in range(16):
+            r = recs[b, w]
+            if int(r[0]) != 0:
+                w0 = int(r[0]) & 0xFFFFFFFFFFFFFFFF
+                code, thr = w0 & 0xFFFFFFFF, (w0 >> 32) & 0x7FFFFFFF
+                a, bb = int(r[1]) & 0xFFFFFFFF, (int(r[1]) >> 32) & 0xFFFFFFFF
+                print(f"  block {b:3d} warp {w:2d} thread {thr:3d}: {CODES.get(code, code)} a={a} (0x{a:x}) b={bb} "
+                      f"clock={int(r[2])} t={int(r[3])}")
+
+
+def main():
+    preset, n = sys.argv[1], int(sys.argv[2])
+    kw = {"three_launch": True} if len(sys.argv) > 3 and sys.argv[3] == "three_launch" else {}
+    B, H, M, w, D, norm, rope = PRESETS[preset]
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    mk = lambda relu: (torch.relu(torch.randn(B, H, M, w, D, generator=g, device=dev)) + 1e-6 if relu  # noqa: E731
+                       else torch.randn(B, H, M, w, D, generator=g, device=dev)).bfloat16()
+    q, k, v = mk(True), mk(True), mk(False)
+    qr, kr = (mk(False), mk(False)) if rope else (None, None)
+    W = (torch.rand(M, M, generator=torch.Generator().manual_seed(4)) / M + 0.5 * torch.eye(M) / M).cuda()
+    L = _capi.lib()
+    diag = torch.zeros(1 + 148 * 64, dtype=torch.int64).pin_memory()
+    if hasattr(L, "mhla_debug_set_diag_buffer"):
+        L.mhla_debug_set_diag_buffer.argtypes = [C.c_void_p]
+        L.mhla_debug_set_diag_buffer.restype = C.c_int
+        assert L.mhla_debug_set_diag_buffer(diag.data_ptr()) == 0
+    first, bad, t0 = None, 0, time.time()
+    try:
+        for i in range(n):
+            out = mhla_b200.mhla(q, k, v, W, q_rope=qr, k_rope=kr, normalize=norm, **kw)
+            if first is None:
+                first = out.clone()
+                sl = lambda t: None if t is None else t[0, 0][None].cpu()  # noqa: E731
+                ref = oracle.blockmix_fwd(sl(q), sl(k), sl(v), W.cpu(), normalize=norm, q_rope=sl(qr), k_rope=sl(kr))
+                print("err vs oracle (unit 0,0):", oracle.err_ratio(ref[0], out[0, 0].float().cpu()), flush=True)
+            elif i % 8 == 0 and not torch.equal(out, first):   # (the comparison syncs: check a sample of the calls)
+                bad += 1
+                if bad <= 3:
+                    d = (out.float() - first.float()).abs()
+                    print("mismatch at iter", i, "max", float(d.max()), "n", int((d > 0).sum()), flush=True)
+        torch.cuda.synchronize()
+        assert torch.equal(out, first) or bad > 0
+        print(f"{preset} {kw or 'fused'}: {n} calls, {bad} sampled mismatches, {time.time() - t0:.1f} s, "
+              f"launches/call {mhla_b200.last_launch_count()}", flush=True)
+    except Exception as e:   # noqa: BLE001
+        print(f"{preset} {kw or 'fused'}: FAILED after {i} calls: {e}", flush=True)
+        decode(diag)
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -15,8 +15,6 @@ normalize = "--no-normalize" not in sys.argv
 kw = {}
 if "--three" in sys.argv:
     kw = dict(three_launch=True)
-if "--fused" in sys.argv:
-    kw = dict(fused=True)
 B, H, M, w, D = 2, 16, 128, 256, 64
 dev = torch.device("cuda")
 g = torch.Generator(device="cuda").manual_seed(0)

@@ -12,7 +12,7 @@ from mhla_b200 import _capi  # noqa: E402
 
 normalize = "--no-normalize" not in sys.argv
 tag = "norm" if normalize else "nonorm"
-kw = dict(fused=True)
+kw = {}
 if "--p1only" in sys.argv:
     kw = dict(debug_flags=_capi.FLAG_STOP_AFTER_P1)
     tag += "_p1only"
