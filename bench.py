@@ -183,11 +183,17 @@ def run_reference_gpu(args):
         normalizer = conv(torch.matmul(q, kt.sum(dim=-1, keepdim=True))) + eps   # :265-266
         return torch.matmul(q, kv) / normalizer                          # :268
 
-    compiled = None
-    try:
-        compiled = torch.compile(core)
-    except Exception as e:   # noqa: BLE001
-        print(f"torch.compile unavailable: {e}", file=sys.stderr)
+    def compiled_core():
+        # a fresh compiled instance per (shape, precision): dynamo otherwise hits its recompile limit over the sweep and
+        # silently falls back to eager
+        try:
+            import torch._dynamo
+            torch._dynamo.reset()
+            return torch.compile(core, dynamic=False)
+        except Exception as e:   # noqa: BLE001
+            print(f"torch.compile unavailable: {e}", file=sys.stderr)
+            return None
+
     for n in ns:
         m = n // WBLK
         row = {"N": n, "M": m, "w": WBLK, "B": B, "H": H, "D": D}
@@ -207,14 +213,16 @@ def run_reference_gpu(args):
             row["ref_eager_tf32_us"] = _timed(lambda: core(q, kt, v, conv, 1e-6), reps)
             with torch.autocast("cuda", dtype=torch.bfloat16):
                 row["ref_eager_bf16_autocast_us"] = _timed(lambda: core(q, kt, v, conv, 1e-6), reps)
-            if compiled is not None:
-                try:
-                    row["ref_compiled_tf32_us"] = _timed(lambda: compiled(q, kt, v, conv, 1e-6), reps)
+            try:
+                cc = compiled_core()
+                if cc is not None:
+                    row["ref_compiled_tf32_us"] = _timed(lambda: cc(q, kt, v, conv, 1e-6), reps)
+                cc = compiled_core()
+                if cc is not None:
                     with torch.autocast("cuda", dtype=torch.bfloat16):
-                        row["ref_compiled_bf16_autocast_us"] = _timed(lambda: compiled(q, kt, v, conv, 1e-6), reps)
-                except Exception as e:   # noqa: BLE001
-                    row["ref_compiled_error"] = repr(e)[:200]
-                    compiled = None
+                        row["ref_compiled_bf16_autocast_us"] = _timed(lambda: cc(q, kt, v, conv, 1e-6), reps)
+            except Exception as e:   # noqa: BLE001
+                row["ref_compiled_error"] = repr(e)[:200]
             del kt
             # context rows at the same B, H, N, D (token-major [B, N, H, D])
             qt = qb.view(B, H, n, D).transpose(1, 2).contiguous()

@@ -88,6 +88,7 @@ struct alignas(64) BlockmixParams {
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
   int o_hint;                               // 1: evict-first L2 hint on the output stores
   int ws_hint;                              // 1: evict-last on the S~ / den stores, evict-first when they are consumed
+  int p2_tma;                               // 1: S~ / den tiles leave by TMA store (lazy publication); 0: 16-byte global stores
   int q_keep;                               // fused mode: the normaliser's Q tiles of the last q_keep groups are loaded
                                             // evict-last and the readout walks the groups backwards (they are still in L2)
   int trace_cta;                            // debug: CTA whose event trace is recorded
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4);
+      mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 4);   // tfull: tcgen05.commit + the issuer's own arrive (see below)
     }
     fence_barrier_init();
     *q_published = 0;
@@ -458,7 +459,17 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
           mma_commit(&tfull[ab]);
-          if (p.normalize) r.advance(D == 64 ? 1 : p.nsub);  // Q stages are consumed by the epilogue warps
+          if (p.normalize) {
+            // The Q stages are consumed by the epilogue warps, but THIS lane waits for them: every fill of every ring
+            // slot must be observed by one role, in order.  mbarrier.try_wait.parity cannot tell "phase k complete"
+            // from "phase k-2 complete": if this lane skipped the Q fills it could later wait on a slot whose previous
+            // (Q) fill is still in flight, pass at once and feed a half-filled stage to the tensor core - the rare
+            // launch failure of round 1 (profiles/r02_stall_root_cause.md).  The arrive below forwards "Q has landed"
+            // to the epilogue through tfull (count 2), which also carries the visibility of the TMA-written tile.
+            const int nq = D == 64 ? 1 : p.nsub;
+            for (int k = 0; k < nq; ++k) { mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full); r.advance(); }
+          }
+          mbar_arrive(&tfull[ab]);
         } else if (it.type == 2) {
           for (int slab = 0; slab < p.kslabs; ++slab) {
             mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
@@ -488,6 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             r.advance();
           }
           mma_commit(&tfull[ab]);
+          mbar_arrive(&tfull[ab]);
         } else {
           Ring r0 = r;
           uint32_t b_addr;
@@ -510,6 +522,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           const int ns = p3_stages<D>(p);
           for (int k = 0; k < ns; ++k) mma_commit(&empty[r0.at(k).idx()]);
           mma_commit(&tfull[ab]);
+          mbar_arrive(&tfull[ab]);
         }
         trace_ev(p, 1, nitem, 2);
         ++nitem;
@@ -651,6 +664,38 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     auto chunk_tma_end = [&]() {
       if (et == 0) tma_store_commit();
       ++nchunk;
+    };
+    // rows of the slot are complete: copy [nrows][128 B] to global memory with plain 16-byte stores of the warpgroup,
+    // row r to gbase + r * row_stride (bytes).  Used for the small S tile of a P1 item: fire-and-forget stores keep the
+    // P1 epilogue short (a TMA store + completion wait costs it ~1200 cycles more, profiles/r02_notes.md).
+    auto chunk_copy = [&](const uint8_t* buf, uint8_t* gbase, size_t row_stride, int nrows, int nvalid) {
+      named_bar_sync(bar_base, kEpiThreads);
+      // thread -> (row = k * 16 + et / 8, 16-byte piece et % 8): a warp instruction covers 4 rows x 128 contiguous bytes
+      const int c = et & 7, r0_ = et >> 3;
+      const uint8_t* sp = buf + r0_ * 128 + ((c ^ (r0_ & 7)) << 4);   // (k * 16 + r0_) & 7 == r0_ & 7
+      uint8_t* gp = gbase + (size_t)r0_ * row_stride + c * 16;
+      auto run = [&](auto KN) {
+        constexpr int kn = decltype(KN)::value;
+        uint4 val[kn];
+#pragma unroll
+        for (int k = 0; k < kn; ++k) val[k] = *reinterpret_cast<const uint4*>(sp + k * 16 * 128);
+#pragma unroll
+        for (int k = 0; k < kn; ++k)
+          if (k * 16 + r0_ < nvalid) __stcg(reinterpret_cast<uint4*>(gp + (size_t)k * 16 * row_stride), val[k]);
+      };
+      if (nrows == 64) run(std::integral_constant<int, 4>{}); else run(std::integral_constant<int, 8>{});
+      ++nchunk;
+    };
+    // every global store of a workspace item has been issued by all 128 threads: publish at once (plus any earlier item
+    // whose TMA stores are still unpublished - those have to land first)
+    auto publish_now = [&]() {
+      named_bar_sync(bar_base + 3, kEpiThreads);
+      ++ndone;
+      if (et == 0) {
+        if (npub + 1 != ndone) { tma_store_wait_all<0>(); fence_proxy_async_all(); }
+        npub = ndone;
+        st_release_cta_shared(&wg_done[wg], npub);
+      }
     };
     // Thread 0 of the warpgroup: every TMA store of the finished workspace items has landed -> publish them.  Called
     // when the thread next looks at the FIFO (the stores were issued an item ago), never on the critical path.
@@ -799,7 +844,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       if (et == 0) trace_ev(p, 2, nitem, 0);
       if (it.type == 1) {
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
-        if (et == 0) { trace_ev(p, 2, nitem, 1); flush(); }
+        if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         // rows of S live in TMEM lanes: D == 128 -> lane = row; D == 64 (M=64 MMA) -> row r in lane 32*(r/16)+r%16
         const bool row_ok = (D == 128) || (lane < 16);
@@ -816,8 +861,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
           named_bar_sync(bar_base + 2, kEpiThreads);  // ksum_s complete
           uint16_t* const nbuf = srow + D * D;        // [hi: wpad][lo: wpad]
+          // (the Q tiles have landed: the issuer waited for them before its arrive on tfull)
           if constexpr (D == 64) {
-            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_q);
             const uint8_t* qs = ring + r.idx() * kStageBytes;
             for (int t = et; t < p.wpad; t += kEpiThreads) {
               uint16_t hi, lo;
@@ -830,7 +875,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             r.advance();
           } else {
             for (int sub = 0; sub < p.nsub; ++sub) {
-              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_q);
               const uint8_t* qs = ring + r.idx() * kStageBytes;
               if (et < p.TW) {
                 const int t = sub * p.TW + et;
@@ -853,30 +897,35 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           load_pack64(acc + c * 64, 1.0f, pk);
           uint8_t* buf = slot_acquire();
           if (row_ok) stage_row(buf, row, pk);
-          chunk_tma_begin();
-          if (et == 0) tma_store_3d(&p.tmSst, buf, c * 64, 0, (int)blk);
-          chunk_tma_end();
+          chunk_copy(buf, reinterpret_cast<uint8_t*>(srow) + c * 128, (size_t)D * 2, D, D);
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        ++ndone;
+        publish_now();
       } else if (it.type == 2) {
         const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
         if (et == 0) { trace_ev(p, 2, nitem, 1); flush(); }
         tc_fence_after();
         const float wsc = p.self_prep ? *wscale_s : __ldg(p.wscale);   // undo the power-of-two normalisation (exact)
-        // (rows beyond the matrix - the last row tile of M = 150 - are clipped by the TMA store)
+        // (rows beyond the matrix - the last row tile of M = 150 - are clipped by the TMA store / the nvalid guard)
+        const int nvalid = p.M - ti * 128;
+        const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
         if (tc < p.n2_scols) {
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
             load_pack64(acc + c * 64, wsc, pk);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
-            chunk_tma_begin();
-            if (et == 0) tma_store_3d_hint(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g, ws_st_hint);
-            chunk_tma_end();
+            if (p.p2_tma) {
+              chunk_tma_begin();
+              if (et == 0) tma_store_3d_hint(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g, ws_st_hint);
+              chunk_tma_end();
+            } else {
+              chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
+                         (size_t)D * D * 2, 128, nvalid);
+            }
           }
         } else {
           for (int q = 0; q < 8; ++q) {
@@ -888,16 +937,22 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * wsc);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, v);
-            chunk_tma_begin();
-            if (et == 0) tma_store_3d_hint(&p.tmDen, buf, col0, ti * 128, it.g, ws_st_hint);
-            chunk_tma_end();
+            if (p.p2_tma) {
+              chunk_tma_begin();
+              if (et == 0) tma_store_3d_hint(&p.tmDen, buf, col0, ti * 128, it.g, ws_st_hint);
+              chunk_tma_end();
+            } else {
+              chunk_copy(buf, reinterpret_cast<uint8_t*>(const_cast<float*>(p.den) + row0 * (size_t)(2 * p.wpad) + col0),
+                         (size_t)2 * p.wpad * 4, 128, nvalid);
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
         r.advance(2 * p.kslabs);
-        ++ndone;
+        if (p.p2_tma) ++ndone;   // lazy: published by flush() once the TMA stores have landed
+        else publish_now();
       } else {
         const int i = it.t;                               // block row within the scheduled (packed) group
         const int gr = it.g * p.pack + it.t / p.M0;       // real (b,h) group and block inside it: tensor coordinates

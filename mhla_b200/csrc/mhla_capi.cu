@@ -79,7 +79,7 @@ constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (sepa
 
 // Tuning / debugging knobs of the blockmix kernel, read from the environment ONCE (first call).
 struct Knobs {
-  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, ws_hint = 1, q_keep = 0, trace_cta = 0, slots = 2;
+  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, ws_hint = 1, q_keep = 0, trace_cta = 0, slots = 2, p2_tma = 1;
   bool no_pack = false, no_self_prep = false;
 };
 const Knobs& knobs() {
@@ -94,6 +94,7 @@ const Knobs& knobs() {
     k.o_hint = geti("MHLA_OHINT", 1);
     k.ws_hint = geti("MHLA_WSHINT", 1);
     k.q_keep = geti("MHLA_QKEEP", 0);
+    k.p2_tma = geti("MHLA_P2TMA", 1);
     k.trace_cta = geti("MHLA_TRACE_CTA", 0);
     k.slots = geti("MHLA_SLOTS", 2) == 1 ? 1 : 2;
     k.no_pack = std::getenv("MHLA_NO_PACK") != nullptr;
@@ -360,6 +361,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.o_hint = kn.o_hint;
   P.ws_hint = kn.ws_hint;
   P.q_keep = kn.q_keep;
+  P.p2_tma = kn.p2_tma;
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -456,6 +458,13 @@ int mhla_blockmix_workspace_init(const mhla_blockmix_desc* d, void* stream_) {
                "cudaMemsetAsync"))
     return MHLA_ERR_CUDA;
   return MHLA_OK;
+}
+
+namespace { __global__ void stall_selftest_kernel() { mhla::report_stall(99, 1, 2); } }
+/* Debug hook: launches one thread that reports a stall (code 99) and traps - checks the diagnostics path end to end. */
+int mhla_debug_trigger_stall(void* stream_) {
+  stall_selftest_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>();
+  return cuda_ok(cudaGetLastError(), "stall_selftest_kernel") ? MHLA_OK : MHLA_ERR_CUDA;
 }
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }

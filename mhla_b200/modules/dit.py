@@ -89,11 +89,19 @@ class _MHLAImage(nn.Module):
         k = torch.relu(self.k_norm(k)) + self.eps
         # "b n w (h d) -> (b h) n w d" as zero-copy views [B, H, M, w, D]
         q5, k5, v5 = (t.reshape(B, M, w, H, D).permute(0, 3, 1, 2, 4) for t in (q, k, v))
-        cdtype = x.dtype if x.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
-        obuf = torch.empty((B, M, w, H, D), dtype=cdtype, device=x.device)
-        mhla_blockmix(q5, k5, v5, self.piece_attn.conv.weight, eps=self.eps, normalize=True,
-                      out=obuf.permute(0, 3, 1, 2, 4))                          # mhla.py:262-268
-        out = obuf.view(B, M, w, H * D).to(x.dtype) + lepe                        # "(b h) n w d -> b n w (h d)"
+        W = self.piece_attn.conv.weight
+        training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)
+        if D in (64, 128) and not training:
+            # inference: the kernel writes straight into the "(b h) n w d -> b n w (h d)" layout (no head-merge copy)
+            cdtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
+            obuf = torch.empty((B, M, w, H, D), dtype=cdtype, device=x.device)
+            mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True, out=obuf.permute(0, 3, 1, 2, 4))   # mhla.py:262-268
+            out = obuf.view(B, M, w, H * D)
+        else:
+            # training (autograd through the operator) or a head dim the shim zero-pads (DiT-XL: 1152 / 16 = 72)
+            o5 = mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True)
+            out = o5.permute(0, 2, 3, 1, 4).reshape(B, M, w, H * D)
+        out = out.to(x.dtype) + lepe                                              # "(b h) n w d -> b n w (h d)"
         out = self.to_out(out)
         return out.view(B, M * w, -1) if squeeze else out
 

@@ -1,4 +1,7 @@
-"""Variant-B module: ``MHLA_Video_Uni`` (mhla_videogen/diffusion/model/wan/mhla_utils.py:158-366).
+"""Variant-B modules: ``MHLA_Video_Uni`` (mhla_videogen/diffusion/model/wan/mhla_utils.py:158-366) and the five further
+MHLA self-attention classes of wan/model.py:428-1390 (``Gated_MHLA_Video``, ``MHLA_Video_Nope``,
+``Gated_MHLA_Video_LePE``, ``MHLA_Video_LePE``, ``MHLA_Video``) - one operator core, different post-processing; the
+registry ``WAN_SELFATTENTION_CLASSES`` below carries the reference's keys (wan/model.py:1592-1605).
 
 Same constructor signature (including the odd positional call ``cls(dim, num_heads, window_size, qk_norm, eps, ...)``
 of wan/model.py:1644-1646, whose third positional lands in ``dim_head`` and is ignored), attributes and
@@ -74,32 +77,53 @@ def rope_apply(x: torch.Tensor, grid_sizes, freqs: torch.Tensor) -> torch.Tensor
     return out
 
 
-class MHLA_Video_Uni(nn.Module):
+class _MHLAVideoBase(nn.Module):
+    """Shared implementation.  Class attributes select what the reference classes differ in (wan/model.py:428-1390 and
+    mhla_utils.py:158-366 were diffed statement by statement: only the post-processing differs):
+      _gate       'always' | 'kwarg' | 'never'   SiLU(g(x)) gate
+      _gnorm      'dim' (RMSNorm over the whole channel dim) | 'head' (per head) | None
+      _lepe       'always' | 'kwarg' | 'never'   depthwise 3x3x3 Conv3d on v
+      _out_norm   True: ``out_rmsnorm`` (RMSNorm over dim after ``o``) when the kwarg is set
+    """
+    _gate, _gnorm, _lepe, _out_norm = "kwarg", "head", "kwarg", False
+
     def __init__(self, dim, num_heads=8, dim_head=None, dropout=0.1, fixed_weight_value=None, qk_norm=True,
                  block_layout=(3, 5, 10), transform="linear", qkv_bias=False, eps=1e-6, is_gated=False, is_lepe=False,
                  **kwargs):
         super().__init__()
+        # (WanAttentionBlock calls cls(dim, num_heads, window_size, qk_norm, eps, ...): window_size lands in dim_head -
+        #  ignored, as in the reference - and eps in fixed_weight_value, wan/model.py:1644-1646)
         dim_head = dim // num_heads
         self.dim = dim
         self.num_heads = num_heads
         self.head_dim = dim_head
+        gated = self._gate == "always" or (self._gate == "kwarg" and is_gated)
+        lepe = self._lepe == "always" or (self._lepe == "kwarg" and is_lepe)
         self.q = nn.Linear(dim, dim)
         self.k = nn.Linear(dim, dim)
         self.v = nn.Linear(dim, dim)
-        self.g = nn.Linear(dim, dim) if is_gated else None
-        self.g_fn = nn.SiLU() if is_gated else None
-        self.g_norm = WanRMSNorm(dim_head, eps=eps)
-        self.is_gated = is_gated
-        self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: g_norm inside the kernel epilogue
-        self.is_lepe = is_lepe
+        if self._gate == "always":
+            self.g, self.g_fn = nn.Linear(dim, dim), nn.SiLU()
+        elif self._gate == "kwarg":
+            self.g, self.g_fn = (nn.Linear(dim, dim), nn.SiLU()) if gated else (None, None)
+        if self._gnorm is not None:
+            self.g_norm = WanRMSNorm(dim if self._gnorm == "dim" else dim_head, eps=eps)
+        self.is_gated = gated
+        self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: per-head g_norm inside the kernel epilogue
+        self.is_lepe = lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.out_norm = kwargs.get("out_rmsnorm", False)
+        if self._out_norm:
+            self.out_rmsnorm = WanRMSNorm(dim, eps=eps) if self.out_norm else nn.Identity()
         self.normalize_out = kwargs.get("normalize_out", True)
         self.blocks_layout = tuple(block_layout)
         self.num_blocks = self.blocks_layout[0] * self.blocks_layout[1] * self.blocks_layout[2]
         self.block_attn = BlockDistanceConv3D(blocks_layout=self.blocks_layout, transform=transform)
-        self.lepe = nn.Conv3d(dim, dim, kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1), groups=dim) if is_lepe else None
+        if self._lepe == "always":
+            self.lepe = nn.Conv3d(dim, dim, kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1), groups=dim)
+        elif self._lepe == "kwarg":
+            self.lepe = nn.Conv3d(dim, dim, kernel_size=(3, 3, 3), stride=1, padding=(1, 1, 1), groups=dim) if lepe else None
         self.eps = eps
         self.o = nn.Linear(dim, dim)
         self.rope_after = kwargs.get("rope_after", False)
@@ -132,7 +156,7 @@ class MHLA_Video_Uni(nn.Module):
         p1, p2, p3 = F_ // fb, H_ // hb, W_ // wb
         nh, D = self.num_heads, self.head_dim
 
-        q, k, v = self.q(x), self.k(x), self.v(x)                                   # :279-288
+        q, k, v = self.q(x), self.k(x), self.v(x)                                   # mhla_utils.py:279-288
         lepe = None
         if self.is_lepe:
             lepe = self.lepe(rearrange(v, "b (f h w) c -> b c f h w", f=F_, h=H_, w=W_))
@@ -147,20 +171,62 @@ class MHLA_Video_Uni(nn.Module):
         pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
         kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
         blk = lambda t: rearrange(t.to(cdtype), pat, **kw).contiguous()           # noqa: E731  (:317-326, one 16-bit copy each)
+        W = self.block_attn.conv.weight
+        training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)
         # the per-head g_norm (:360-364) is fused into the kernel's readout epilogue (fp32, before the single rounding)
-        fuse = dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps) if self.fuse_out_norm else {}
+        fuse_norm = self._gnorm == "head" and self.fuse_out_norm and not training and D in (64, 128)
+        fuse = dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps) if fuse_norm else {}
         if self.normalize_out:
-            out = mhla_blockmix(blk(q), blk(k), blk(v), self.block_attn.conv.weight, q_rope=blk(q_rope),
-                                k_rope=blk(k_rope), eps=self.eps, normalize=True, **fuse)
+            out = mhla_blockmix(blk(q), blk(k), blk(v), W, q_rope=blk(q_rope), k_rope=blk(k_rope), eps=self.eps,
+                                normalize=True, **fuse)
         else:  # shipped Wan config (norm_output: false): the un-roped q/k are not needed at all
-            out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), self.block_attn.conv.weight, eps=self.eps,
-                                normalize=False, **fuse)
+            out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), W, eps=self.eps, normalize=False, **fuse)
         out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
-        if not self.fuse_out_norm:
+        if self._gnorm == "head" and not fuse_norm:
             out = self.g_norm(out)                                                  # :360-364 per-head RMSNorm
         out = out.reshape(B, N, C)
+        if self._gnorm == "dim":
+            out = self.g_norm(out)                                                  # wan/model.py:617 (whole channel dim)
         if self.is_gated:
             out = out * self.g_fn(self.g(x))
         if self.is_lepe:
             out = out + lepe
-        return self.o(out)
+        out = self.o(out)
+        return self.out_rmsnorm(out) if self._out_norm else out
+
+
+class MHLA_Video_Uni(_MHLAVideoBase):
+    """mhla_utils.py:158-366: optional gate / LePE (kwargs), per-head g_norm."""
+    _gate, _gnorm, _lepe, _out_norm = "kwarg", "head", "kwarg", False
+
+
+class Gated_MHLA_Video(_MHLAVideoBase):
+    """wan/model.py:428-619: always gated, g_norm over the whole channel dim."""
+    _gate, _gnorm, _lepe, _out_norm = "always", "dim", "never", False
+
+
+class MHLA_Video_Nope(_MHLAVideoBase):
+    """wan/model.py:621-806: no gate, optional ``out_rmsnorm`` after ``o``."""
+    _gate, _gnorm, _lepe, _out_norm = "never", None, "never", True
+
+
+class Gated_MHLA_Video_LePE(_MHLAVideoBase):
+    """wan/model.py:808-1008: gate, per-head g_norm, LePE added before ``o``."""
+    _gate, _gnorm, _lepe, _out_norm = "always", "head", "always", False
+
+
+class MHLA_Video_LePE(_MHLAVideoBase):
+    """wan/model.py:1010-1203: LePE, optional ``out_rmsnorm``."""
+    _gate, _gnorm, _lepe, _out_norm = "never", None, "always", True
+
+
+class MHLA_Video(_MHLAVideoBase):
+    """wan/model.py:1205-1390: plain (optional ``out_rmsnorm``)."""
+    _gate, _gnorm, _lepe, _out_norm = "never", None, "never", True
+
+
+# the MHLA entries of wan/model.py:1592-1605; a maintainer updates the reference's dict with this one
+WAN_SELFATTENTION_CLASSES = {
+    "mhla": MHLA_Video, "gated_mhla": Gated_MHLA_Video, "mhla_nope": MHLA_Video_Nope, "mhla_lepe": MHLA_Video_LePE,
+    "gated_mhla_lepe": Gated_MHLA_Video_LePE, "mhla_uni": MHLA_Video_Uni,
+}

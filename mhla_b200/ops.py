@@ -90,11 +90,30 @@ def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
     return _capi.Tensor5(t.data_ptr(), sb, sh, sm, sw)
 
 
+def _needs_grad(*tensors) -> bool:
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
 def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
+                  out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+    """Non-causal block-mixed MHLA (see ``_blockmix_fwd`` for the arguments).  Differentiable: when gradients are
+    enabled and an input requires them the call goes through ``autograd.BlockmixFunction`` (CUDA forward, analytic
+    backward for q, k, v, q_rope, k_rope and the mixing matrix); ``out=`` and the fused output RMSNorm are
+    inference-only and raise instead of silently dropping the graph."""
+    if _needs_grad(q, k, v, mix, q_rope, k_rope, out_rms_weight):
+        if out is not None or out_rms_weight is not None:
+            raise NotImplementedError("out= / out_rms_weight are inference-only; call without them when training")
+        from .autograd import BlockmixFunction
+        return BlockmixFunction.apply(q, k, v, mix, q_rope, k_rope, float(eps), bool(normalize), kw)
+    return _blockmix_fwd(q, k, v, mix, q_rope=q_rope, k_rope=k_rope, eps=eps, normalize=normalize, out=out,
+                         out_rms_weight=out_rms_weight, **kw)
+
+
+def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                   out: Optional[torch.Tensor] = None, fused: bool = True, unfused: Optional[bool] = None,
                   three_launch: bool = False, two_launch: bool = False, force_fused: bool = False, debug_flags: int = 0,
                   out_rms_weight: Optional[torch.Tensor] = None, out_rms_eps: float = 1e-6) -> torch.Tensor:
-    """Non-causal block-mixed MHLA forward on block-major tensors.
+    """Non-causal block-mixed MHLA forward on block-major tensors (no autograd graph).
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
               with fp32 accumulation and returned as fp32).  Strided views are consumed in place when every
@@ -108,6 +127,9 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
               the same kernel (an independent cross-check), ``two_launch`` as summaries+mixing followed by the readout.
     """
     _require_cuda(q, k, v, mix, q_rope, k_rope)
+    q, k, v = q.detach(), k.detach(), v.detach()
+    q_rope = None if q_rope is None else q_rope.detach()
+    k_rope = None if k_rope is None else k_rope.detach()
     if (q_rope is None) != (k_rope is None):
         raise ValueError("q_rope and k_rope must be given together")
     in_dtype = q.dtype
@@ -271,25 +293,40 @@ def _t4(t: torch.Tensor) -> _capi.Tensor4:
 
 def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
                 unfused: Optional[bool] = None) -> torch.Tensor:
+    """Causal chunked MHLA (see ``_causal_fwd``); differentiable through ``autograd.CausalFunction``."""
+    if _needs_grad(q, k, v, mixing_matrix):
+        from .autograd import CausalFunction
+        return CausalFunction.apply(q, k, v, mixing_matrix, int(chunk_size), scale, unfused)
+    return _causal_fwd(q, k, v, mixing_matrix, chunk_size=chunk_size, scale=scale, unfused=unfused)
+
+
+def _causal_fwd(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
+                unfused: Optional[bool] = None) -> torch.Tensor:
     """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype.
 
     T is zero-padded to a multiple of the chunk exactly as the reference does (naive.py:46-51); the pad is a host-side
     copy that only happens for ragged T."""
     _require_cuda(q, k, v, mixing_matrix)
+    q, k, v = q.detach(), k.detach(), v.detach()
     in_dtype = q.dtype
     cdtype = in_dtype if in_dtype in _DT else torch.bfloat16
-    B, T_in, H, K = q.shape
-    V = v.shape[-1]
+    B, T_in, H, K_in = q.shape
+    V_in = v.shape[-1]
+    # head dims between the kernel's widths run zero-padded (exact: padded channels add zeros to q.k and to S)
+    K = 64 if K_in <= 64 else 128
+    V = 64 if V_in <= 64 else (128 if V_in <= 128 else 256)
+    if K_in > 128 or V_in > 256:
+        raise _capi.MhlaError(f"unsupported causal head dims K={K_in} V={V_in} (K <= 128, V <= 256)")
     pad = (chunk_size - T_in % chunk_size) % chunk_size
     T = T_in + pad
 
-    def prep(t):
+    def prep(t, dpad):
         t = t.to(cdtype) if t.dtype != cdtype else t
-        if pad:
-            t = torch.nn.functional.pad(t, (0, 0, 0, 0, 0, pad))
+        if pad or dpad:
+            t = torch.nn.functional.pad(t, (0, dpad, 0, 0, 0, pad))
         return t if _tma_ok(t) else t.contiguous()
 
-    q4, k4, v4 = prep(q), prep(k), prep(v)
+    q4, k4, v4 = prep(q, K - K_in), prep(k, K - K_in), prep(v, V - V_in)
     o4 = torch.empty((B, T, H, V), dtype=cdtype, device=q.device)
     Lm = mixing_matrix.shape[0]
     mm = mixing_matrix.detach().reshape(Lm, mixing_matrix.shape[1]).to(torch.float32).contiguous()
@@ -300,7 +337,7 @@ def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
     d.B, d.T, d.H, d.K, d.V = B, T, H, K, V
     # unfused: None = let the library choose (three launches for large batches), True / False force either structure
     d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], (0 if unfused is None else (_capi.FLAG_UNFUSED if unfused else _capi.FLAG_FUSED))
-    d.scale = float(K ** -0.5 if scale is None else scale)
+    d.scale = float(K_in ** -0.5 if scale is None else scale)
     d.q, d.k, d.v, d.out = _t4(q4), _t4(k4), _t4(v4), _t4(o4)
     d.mm, d.mm_ld, d.L = mm.data_ptr(), mm.stride(0), Lm
     L = _capi.lib()
@@ -313,8 +350,8 @@ def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
         _capi.check(L.mhla_fwd_causal(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_causal")
     for t in (q4, k4, v4, mm, ws):
         t.record_stream(torch.cuda.current_stream())
-    if pad:
-        o4 = o4[:, :T_in]
+    if pad or V != V_in:
+        o4 = o4[:, :T_in, :, :V_in]
     return o4 if in_dtype == cdtype else o4.to(in_dtype)
 
 

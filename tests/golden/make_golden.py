@@ -35,7 +35,12 @@ def _load(path, name):
     return mod
 
 
+ONLY = set(sys.argv[1:])      # optional fixture names: regenerate just those
+
+
 def save(name, **arrays):
+    if ONLY and name not in ONLY:
+        return
     out = {}
     for k, v in arrays.items():
         if isinstance(v, torch.Tensor):
@@ -107,7 +112,7 @@ def golden_variant_a():
 # ---------------------------------------------------------------------------------------------------
 # variant B : mhla_videogen/diffusion/model/wan/mhla_utils.py (MHLA_Video_Uni)
 # ---------------------------------------------------------------------------------------------------
-def golden_variant_b():
+def golden_variant_b_stubs():
     class WanRMSNorm(torch.nn.Module):   # verbatim behaviour of wan/model.py:181-196 (stub for the heavy import)
         def __init__(self, dim, eps=1e-5):
             super().__init__()
@@ -123,6 +128,10 @@ def golden_variant_b():
     for name in ["diffusion", "diffusion.model", "diffusion.model.wan", "diffusion.model.wan.model"]:
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["diffusion.model.wan.model"].WanRMSNorm = WanRMSNorm
+
+
+def golden_variant_b():
+    golden_variant_b_stubs()
     mu = _load(os.path.join(REF, "mhla_videogen/diffusion/model/wan/mhla_utils.py"), "ref_mhla_utils")
 
     ws = {}
@@ -188,6 +197,65 @@ def golden_variant_b():
 
 
 # ---------------------------------------------------------------------------------------------------
+# variant B' : the five further MHLA self-attention classes of wan/model.py:428-1390 (registry :1592-1605)
+# ---------------------------------------------------------------------------------------------------
+def golden_variant_b_prime():
+    """wan/model.py cannot be imported here (diffusers / mmcv / ... are not installed), so the five class definitions
+    are cut out of the reference file by AST and executed unmodified in a namespace that provides exactly the names
+    they use: torch / nn / rearrange, the reference's own BlockDistanceConv3D and rope_apply (mhla_utils.py, loaded as
+    in golden_variant_b) and WanRMSNorm (also cut from model.py:181-196)."""
+    import ast
+    golden_variant_b_stubs()
+    mu = _load(os.path.join(REF, "mhla_videogen/diffusion/model/wan/mhla_utils.py"), "ref_mhla_utils_bp")
+    path = os.path.join(REF, "mhla_videogen/diffusion/model/wan/model.py")
+    src = open(path).read()
+    tree = ast.parse(src)
+    names = ["WanRMSNorm", "Gated_MHLA_Video", "MHLA_Video_Nope", "Gated_MHLA_Video_LePE", "MHLA_Video_LePE", "MHLA_Video"]
+    ns = {"torch": torch, "nn": torch.nn, "rearrange": rearrange, "BlockDistanceConv3D": mu.BlockDistanceConv3D,
+          "rope_apply": mu.rope_apply, "__name__": "ref_wan_model_cut"}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in names:
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+
+    def rope_params(max_seq_len, dim, theta=10000):          # wan/model.py:139-146
+        freqs = torch.outer(torch.arange(max_seq_len),
+                            1.0 / torch.pow(theta, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+        return torch.polar(torch.ones_like(freqs), freqs)
+
+    dim, heads, layout, grid = 128, 2, (1, 2, 2), (2, 4, 8)
+    d = dim // heads
+    freqs = torch.cat([rope_params(1024, d - 4 * (d // 6)), rope_params(1024, 2 * (d // 6)),
+                       rope_params(1024, 2 * (d // 6))], dim=1)
+    for key, cls, kw in [("gated_mhla", "Gated_MHLA_Video", dict(normalize_out=True)),
+                         ("mhla_nope", "MHLA_Video_Nope", dict(normalize_out=False, out_rmsnorm=True)),
+                         ("gated_mhla_lepe", "Gated_MHLA_Video_LePE", dict(normalize_out=False)),
+                         ("mhla_lepe", "MHLA_Video_LePE", dict(normalize_out=True, out_rmsnorm=False)),
+                         ("mhla", "MHLA_Video", dict(normalize_out=False, out_rmsnorm=True))]:
+        torch.manual_seed(5)
+        # the positional call of WanAttentionBlock (wan/model.py:1644-1646): window_size lands in dim_head, qk_norm in
+        # dropout, eps in fixed_weight_value (-> every weight starts at 1e-6; re-randomised below like a checkpoint load)
+        m = ns[cls](dim, heads, (-1, -1), True, 1e-6, rope_after=False, without_rope=False, power=1.0,
+                    out_rmsnorm=kw.get("out_rmsnorm", False), normalize_out=kw["normalize_out"], is_gated=False,
+                    is_lepe=False, block_layout=layout).eval()
+        for n_, p in m.named_parameters():
+            if n_ == "block_attn.conv.weight":
+                p.data = mu.BlockDistanceConv3D(blocks_layout=layout).conv.weight.data * (1.0 + 0.1 * torch.rand_like(p))
+            elif n_.endswith("weight") and p.dim() == 1:
+                p.data = 1.0 + 0.1 * torch.randn_like(p)
+            elif p.dim() >= 2:
+                p.data = torch.randn_like(p) * (p.shape[1] ** -0.5 if p.dim() == 2 else 0.2)
+            else:
+                p.data = 0.1 * torch.randn_like(p)
+        B = 2
+        N = grid[0] * grid[1] * grid[2]
+        x = torch.randn(B, N, dim)
+        y = m(x, torch.tensor([N] * B), torch.tensor([list(grid)] * B, dtype=torch.long), freqs)
+        sd = {f"sd.{k_}": v_ for k_, v_ in m.state_dict().items()}
+        save("bp_" + key, x=x, y=y, heads=np.int32(heads), layout=np.array(layout), grid=np.array(grid),
+             normalize_out=np.int32(kw["normalize_out"]), out_rmsnorm=np.int32(kw.get("out_rmsnorm", False)), **sd)
+
+
+# ---------------------------------------------------------------------------------------------------
 # variant C : mhla_nlp/fla/ops/mhla/naive.py
 # ---------------------------------------------------------------------------------------------------
 def golden_variant_c():
@@ -218,9 +286,17 @@ def golden_variant_c():
     o, S = nv.naive_recurrent_mhla(q, k, v, init)
     o_chunk = nv.naive_chunk_simple_mhla_fixed(q, k, v, init)
     save("c_recurrent_t48", q=q, k=k, v=v, mm=init.view(L, L), o=o, o_chunk=o_chunk, S=S)
+    # the same with a head shape inside the kernel envelope (K=64, V=128), a ragged T < 64 and a random mixing matrix
+    g = torch.Generator().manual_seed(5)
+    q, k, v = torch.randn(2, 57, 2, 64, generator=g), torch.randn(2, 57, 2, 64, generator=g), torch.randn(2, 57, 2, 128, generator=g)
+    mm = torch.clamp(torch.rand(L, L, generator=g), 1e-5, 1).tril().view(L, L, 1, 1, 1, 1)
+    o, S = nv.naive_recurrent_mhla(q, k, v, mm)
+    o_chunk = nv.naive_chunk_simple_mhla_fixed(q, k, v, mm)
+    save("c_recurrent_k64", q=q, k=k, v=v, mm=mm.view(L, L), o=o, o_chunk=o_chunk)
 
 
 if __name__ == "__main__":
     golden_variant_a()
     golden_variant_b()
+    golden_variant_b_prime()
     golden_variant_c()

@@ -1,6 +1,7 @@
 """GPU parity tests for the causal chunked operator (variant C) vs the CPU oracle and the reference's golden outputs.
-Tolerance: bf16 I/O with fp32 accumulation; intermediate chunk summaries and the masked intra-chunk scores are rounded
-to bf16 (as the reference's bf16-autocast path does), so RMS error ratio <= 1e-2 and max-abs <= 4e-2 * max|ref|."""
+Tolerance: bf16 I/O with fp32 accumulation against the fp32 oracle on the same bf16-rounded inputs:
+RMS error ratio <= 5e-3 and max-abs <= 2e-2 * max|ref|.  Yardstick (profiles/r02_causal_yardstick.log): the reference's
+own operator under bf16 autocast sits at 2.5e-3 .. 3.3e-3 RMS / 3.5e-3 .. 4.4e-3 max on these shapes."""
 import pytest
 import torch
 
@@ -10,7 +11,7 @@ from conftest import load_golden
 pytestmark = pytest.mark.gpu
 
 
-def _check(ref, out, rms=1e-2, mx=4e-2):
+def _check(ref, out, rms=5e-3, mx=2e-2):
     out = out.float().cpu()
     assert not torch.isnan(out).any()
     assert out.shape == ref.shape
@@ -53,25 +54,32 @@ def test_causal_vs_oracle(B, T, H, K, V, signed, init, unfused):
 @pytest.mark.parametrize("name", ["c_t256", "c_t200_ragged", "c_kv_128_256"])
 def test_causal_vs_reference_golden(name):
     import mhla_b200
-    g = load_golden(name)
-    if g["q"].shape[-1] not in (64, 128):
-        pytest.skip("fixture head dim outside the kernel envelope (oracle-only fixture)")
+    g = load_golden(name)        # (K = 32 fixtures run zero-padded to 64 channels inside the shim)
     q, k, v = g["q"].bfloat16(), g["k"].bfloat16(), g["v"].bfloat16()
     mm6 = g["mm"].view(32, 32, 1, 1, 1, 1)                          # the layer's parameter shape (layers/mhla.py:200)
     out = mhla_b200.naive_chunk_simple_mhla_fixed(q.cuda(), k.cuda(), v.cuda(), mm6.cuda())
     ref = oracle.causal_chunk_fwd(q.float(), k.float(), v.float(), g["mm"])
     _check(ref, out)
-    _check(g["o"], out, rms=2e-2, mx=8e-2)                          # vs the reference's fp32 result on un-rounded inputs
+    _check(g["o"], out, rms=1e-2, mx=4e-2)                          # vs the reference's fp32 result on un-rounded inputs
 
 
-def test_recurrent_first_chunk_and_errors():
+@pytest.mark.parametrize("name", ["c_recurrent_t48", "c_recurrent_k64"])
+def test_recurrent_first_chunk_vs_reference_golden(name):
+    """naive_recurrent_mhla (naive.py:88-142) for T <= 64, the only regime the layer uses it in: the reference's own
+    token-recurrent output AND its chunk output (they agree there) against the kernel."""
     import mhla_b200
-    g = load_golden("c_recurrent_t48")
-    if g["q"].shape[-1] in (64, 128):
-        o, s = mhla_b200.naive_recurrent_mhla(g["q"].bfloat16().cuda(), g["k"].bfloat16().cuda(),
-                                              g["v"].bfloat16().cuda(), g["mm"].cuda())
-        assert s is None
-        _check(g["o"], o, rms=2e-2, mx=8e-2)
+    g = load_golden(name)
+    q, k, v = g["q"].bfloat16(), g["k"].bfloat16(), g["v"].bfloat16()
+    o, s = mhla_b200.naive_recurrent_mhla(q.cuda(), k.cuda(), v.cuda(), g["mm"].view(32, 32, 1, 1, 1, 1).cuda())
+    assert s is None
+    ref = oracle.causal_chunk_fwd(q.float(), k.float(), v.float(), g["mm"])
+    _check(ref, o)
+    _check(g["o"], o, rms=1e-2, mx=4e-2)
+    _check(g["o_chunk"], o, rms=1e-2, mx=4e-2)
+
+
+def test_recurrent_errors():
+    import mhla_b200
     q = torch.zeros(1, 64 * 33, 1, 64, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(IndexError):
         mhla_b200.mhla_causal(q, q, q, torch.ones(32, 32, device="cuda").tril())

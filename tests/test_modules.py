@@ -5,7 +5,7 @@ import torch
 
 import oracle
 from conftest import load_golden
-from mhla_b200.modules import MHLA, MHLA4DiT, MHLA_Normed_Torch, MHLA_Video_Uni, rope_apply
+from mhla_b200.modules import MHLA, MHLA4DiT, MHLA_Normed_Torch, MHLA_Video_Uni, WAN_SELFATTENTION_CLASSES, rope_apply
 
 
 def _sd(g):
@@ -24,10 +24,22 @@ def _build(name, g):
         return MHLA_Video_Uni(g["x"].shape[-1], int(g["heads"]), None, 0.0, None, True,
                               tuple(int(v) for v in g["layout"]), normalize_out=bool(g["normalize_out"]),
                               is_gated=bool(g["gated"]))
+    if name.startswith("bp_"):      # the positional call of WanAttentionBlock (wan/model.py:1644-1646)
+        return WAN_SELFATTENTION_CLASSES[name[3:]](
+            g["x"].shape[-1], int(g["heads"]), (-1, -1), True, 1e-6, rope_after=False, without_rope=False, power=1.0,
+            out_rmsnorm=bool(g["out_rmsnorm"]), normalize_out=bool(g["normalize_out"]), is_gated=False, is_lepe=False,
+            block_layout=tuple(int(v) for v in g["layout"]))
     raise KeyError(name)
 
 
-@pytest.mark.parametrize("name", ["a_dit_s2", "a_qknorm", "a_vit_twin", "b_norm", "b_nonorm"])
+BPRIME = ["bp_mhla", "bp_gated_mhla", "bp_mhla_nope", "bp_mhla_lepe", "bp_gated_mhla_lepe"]
+
+
+def test_wan_registry_keys():
+    assert set(WAN_SELFATTENTION_CLASSES) == {"mhla", "gated_mhla", "mhla_nope", "mhla_lepe", "gated_mhla_lepe", "mhla_uni"}
+
+
+@pytest.mark.parametrize("name", ["a_dit_s2", "a_qknorm", "a_vit_twin", "b_norm", "b_nonorm"] + BPRIME)
 def test_state_dict_keys_match_reference(name):
     g = load_golden(name)
     m = _build(name, g)
@@ -89,7 +101,7 @@ def _fwd_err(name, atol_scale=1.0):
     m = m.cuda()
     x = g["x"].cuda()
     with torch.no_grad():
-        if name.startswith("b_"):
+        if name.startswith("b_") or name.startswith("bp_"):
             B = x.shape[0]
             grid = torch.tensor([[int(v) for v in g["grid"]]] * B, dtype=torch.long)
             d = x.shape[-1] // int(g["heads"])
@@ -101,11 +113,60 @@ def _fwd_err(name, atol_scale=1.0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["a_dit_s2", "b_nonorm"])
+@pytest.mark.parametrize("name", ["a_dit_s2", "a_qknorm", "a_vit_twin", "b_norm", "b_nonorm"] + BPRIME)
 def test_module_forward_matches_reference_module(name):
     """Whole-module forward (fp32 weights, operator in bf16) vs the reference module's recorded fp32 output.
-    Budget: the operator's 5e-3 plus bf16 rounding of q,k,v (2^-9 each)."""
+    Budget: the operator's 5e-3 plus bf16 rounding of q,k,v (2^-9 each).  The D = 32 fixtures run zero-padded."""
     assert _fwd_err(name) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_dit_module_padded_head_dim_and_fp16_autocast():
+    """DiT-XL heads (1152 / 16 = 72 channels) through the MODULE (the shim zero-pads; no out= view), and fp16 autocast
+    (LayerNorm returns fp32, the projections fp16: the output buffer follows q's dtype)."""
+    torch.manual_seed(0)
+    m = MHLA4DiT(144, heads=2, dropout=0.0, block_size=16, embed_len=64, qkv_bias=True).eval().cuda()
+    x = torch.randn(2, 4, 16, 144, device="cuda")
+    with torch.no_grad():
+        y = m(x)
+        xn = m.norm(x)
+        q, k, v, lepe = m._mlp_lepe(xn)
+        q, k = torch.relu(q) + m.eps, torch.relu(k) + m.eps
+        sp = lambda t: t.reshape(2, 4, 16, 2, 72).permute(0, 3, 1, 2, 4).float().cpu()   # noqa: E731
+        o = oracle.blockmix_fwd(sp(q), sp(k), sp(v), m.piece_attn.get_weight_matrix().cpu(), eps=m.eps)
+        ref = m.to_out(o.permute(0, 2, 3, 1, 4).reshape(2, 4, 16, 144).cuda() + lepe)
+        assert oracle.err_ratio(ref.float().cpu(), y.float().cpu()) < 1.5e-2
+        m64 = MHLA4DiT(128, heads=2, dropout=0.0, block_size=16, embed_len=64).eval().cuda()
+        with torch.autocast("cuda", dtype=torch.float16):
+            y16 = m64(torch.randn(2, 4, 16, 128, device="cuda"))
+        assert torch.isfinite(y16.float()).all()
+
+
+@pytest.mark.gpu
+def test_modules_train_through_the_operator():
+    """loss.backward() reaches the projections AND the trainable mixing matrix (the reference trainers clamp
+    piece_attn.conv.weight after every step, mhla_dit/train.py:308-310); gradients match the oracle's autograd."""
+    torch.manual_seed(0)
+    m = MHLA4DiT(128, heads=2, dropout=0.0, block_size=16, embed_len=64, qkv_bias=True).cuda()
+    x = torch.randn(2, 4, 16, 128, device="cuda")
+    y = m(x)
+    y.square().mean().backward()
+    gW = m.piece_attn.conv.weight.grad
+    assert gW is not None and float(gW.abs().sum()) > 0 and m.to_qkv.weight.grad is not None
+
+    # the same forward with the oracle in the operator's place, on CPU in fp32
+    mc = MHLA4DiT(128, heads=2, dropout=0.0, block_size=16, embed_len=64, qkv_bias=True)
+    mc.load_state_dict({k_: v_.cpu() for k_, v_ in m.state_dict().items()})
+    xc = x.cpu()
+    xn = mc.norm(xc)
+    q, k, v, lepe = mc._mlp_lepe(xn)
+    q, k = torch.relu(q) + mc.eps, torch.relu(k) + mc.eps
+    sp = lambda t: t.reshape(2, 4, 16, 2, 64).permute(0, 3, 1, 2, 4)   # noqa: E731
+    o = oracle.blockmix_fwd(sp(q), sp(k), sp(v), mc.piece_attn.conv.weight.view(4, 4), eps=mc.eps)
+    yc = mc.to_out(o.permute(0, 2, 3, 1, 4).reshape(2, 4, 16, 128) + lepe)
+    yc.square().mean().backward()
+    assert oracle.err_ratio(mc.piece_attn.conv.weight.grad, gW.cpu()) < 3e-2
+    assert oracle.err_ratio(mc.to_qkv.weight.grad, m.to_qkv.weight.grad.cpu()) < 3e-2
 
 
 @pytest.mark.gpu

@@ -90,13 +90,15 @@ def test_variant_c_chunk(name):
         assert oracle.err_ratio(g["o"], closed) < 1e-5
 
 
-def test_variant_c_recurrent_first_chunk():
-    g = load_golden("c_recurrent_t48")
+@pytest.mark.parametrize("name", ["c_recurrent_t48", "c_recurrent_k64"])
+def test_variant_c_recurrent_first_chunk(name):
+    g = load_golden(name)
     o, state = oracle.recurrent_first_chunk_fwd(g["q"], g["k"], g["v"], g["mm"])
     assert state is None
     assert oracle.err_ratio(g["o"], o) < 1e-5          # reference recurrent form
     assert oracle.err_ratio(g["o_chunk"], o) < 2e-6    # reference chunk form
-    assert float(g["S"].abs().max()) == 0.0            # the reference's "final state" is all zeros
+    if "S" in g:
+        assert float(g["S"].abs().max()) == 0.0        # the reference's "final state" is all zeros
 
 
 def test_variant_c_needs_enough_mixing_rows():

@@ -24,6 +24,15 @@ PRESETS = {
     "headline": (2, 16, 128, 256, 64, True, False),
     "dit64": (64, 6, 16, 16, 64, True, False),
     "small_rope": (1, 3, 20, 210, 128, True, True),
+    # variations of wan_norm that isolate what the launch failure needs
+    "rn_d64": (2, 12, 150, 210, 64, True, True),
+    "n_d128": (2, 12, 150, 210, 128, True, False),
+    "r_d128": (2, 12, 150, 210, 128, False, True),
+    "rn_w256": (2, 12, 150, 256, 128, True, True),
+    "rn_w128": (2, 12, 150, 128, 128, True, True),
+    "rn_m128": (2, 12, 128, 210, 128, True, True),
+    "rn_m64": (2, 12, 64, 210, 128, True, True),
+    "rn_b1": (1, 12, 150, 210, 128, True, True),
 }
 CODES = {1: "mbarrier", 2: "item stream", 3: "scheduler throttle", 4: "scheduler idle", 5: "signal warp", 6: "counter spin"}
 
@@ -44,7 +53,26 @@ def decode(diag):
                       f"clock={int(r[2])} t={int(r[3])}")
 
 
+def selftest():
+    """The diagnostics path end to end: a one-thread kernel reports a stall and traps; the record must be readable."""
+    L = _capi.lib()
+    diag = torch.zeros(1 + 148 * 64, dtype=torch.int64).pin_memory()
+    torch.zeros(1, device="cuda")
+    L.mhla_debug_set_diag_buffer.argtypes = [C.c_void_p]
+    assert L.mhla_debug_set_diag_buffer(diag.data_ptr()) == 0
+    L.mhla_debug_trigger_stall.argtypes = [C.c_void_p]
+    L.mhla_debug_trigger_stall(None)
+    try:
+        torch.cuda.synchronize()
+        print("selftest: no error raised?!")
+    except Exception as e:   # noqa: BLE001
+        print("selftest: error as expected:", str(e).splitlines()[0])
+    decode(diag)
+
+
 def main():
+    if sys.argv[1] == "selftest":
+        return selftest()
     preset, n = sys.argv[1], int(sys.argv[2])
     kw = {"three_launch": True} if len(sys.argv) > 3 and sys.argv[3] == "three_launch" else {}
     B, H, M, w, D, norm, rope = PRESETS[preset]
@@ -80,7 +108,7 @@ def main():
         print(f"{preset} {kw or 'fused'}: {n} calls, {bad} sampled mismatches, {time.time() - t0:.1f} s, "
               f"launches/call {mhla_b200.last_launch_count()}", flush=True)
     except Exception as e:   # noqa: BLE001
-        print(f"{preset} {kw or 'fused'}: FAILED after {i} calls: {e}", flush=True)
+        print(f"{preset} {kw or 'fused'}: FAILED after {i} calls, {time.time() - t0:.1f} s: {str(e).splitlines()[0]}", flush=True)
         decode(diag)
         sys.exit(1)
 
