@@ -267,6 +267,7 @@ def main():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the extra timed loop with the all-gather of the outputs")
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
     args = ap.parse_args()
@@ -313,12 +314,25 @@ def main():
     gathered = torch.empty((UNITS, M, WBLK, D), dtype=torch.bfloat16, device=dev) if world > 1 else None
     it = [0]
 
-    def step(gather=False):
-        q, k, v, out = sets[it[0] % nsets]
-        it[0] += 1
+    def launch(i, gather=False):
+        q, k, v, out = sets[i % nsets]
         mhla_sharded(q, k, v, W, inputs="local", total_units=UNITS, gather=False, normalize=normalize, out=out, **path_kw)
         if gather:
             dist.all_gather_into_tensor(gathered, out)
+
+    # A step = one launch of the operator on this rank's units.  The launches are replayed from CUDA graphs (one per
+    # rotating input set, captured after warm-up) so that the Python / ctypes enqueue cost (~25 us per call) does not
+    # sit on the timed path when the sharded kernel itself only takes 30-40 us (N = 8); `--no-graph` times eager calls.
+    graphs = []
+    it = [0]
+
+    def step(gather=False):
+        i = it[0]
+        it[0] += 1
+        if graphs and not gather:
+            graphs[i % nsets].replay()
+        else:
+            launch(i, gather)
 
     # quick self-check of one (b,h) unit against the oracle before timing anything
     step()
@@ -328,6 +342,19 @@ def main():
     if not err < 5e-3:
         raise SystemExit(f"bench self-check failed: err_ratio {err}")
     it[0] = 0
+    if not args.no_graph:
+        try:
+            for i in range(nsets):
+                launch(i)                                  # warm every set's descriptors / workspace
+            torch.cuda.synchronize()
+            for i in range(nsets):
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr):
+                    launch(i)
+                graphs.append(gr)
+        except Exception as e:   # noqa: BLE001
+            print(f"CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
+            graphs.clear()
 
     def timed_loop(gather):
         for _ in range(warm):
@@ -398,6 +425,7 @@ def main():
             "workload": f"blockmix A (mhla_dit core): B={B} H={H} N={N} D={D} w={WBLK} M={M} normalize={int(normalize)} (whole job)",
             "parallelism": (f"{UNITS} (b,h) units sharded over {world} rank(s), {nloc} per GPU, no data-path collective"
                             + ("; with_gather adds one NCCL all_gather_into_tensor of the outputs behind the kernel" if ms_gather else "")),
+            "launch": "CUDA-graph replay of one operator launch per step" if graphs else "eager launch per step",
             "l2": (f"{nsets} rotating input/output set(s) of {set_bytes / 1e6:.0f} MB per rank: working set "
                    f"{nsets * set_bytes / 1e6:.0f} MB > 126 MB L2 (no explicit flush)"),
         },

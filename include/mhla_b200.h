@@ -53,6 +53,8 @@ enum {
                                  * calls carrying this flag since.  The fused kernel then needs no prologue launch (its
                                  * CTAs split the mixing matrix themselves and the last one to finish re-zeroes the
                                  * control block): ONE launch per call.  Ignored by the multi-launch paths. */
+  MHLA_FLAG_NO_SMALLN = 1 << 15, /* do not take the short-sequence kernel (M*w <= 256 tokens per unit, D = 64: the whole
+                                 * unit is processed on chip by one CTA, no workspace); used by the tests as a cross-check */
   MHLA_FLAG_STOP_AFTER_P1 = 1 << 9,  /* debugging (with UNFUSED): stop after the block summaries */
   MHLA_FLAG_STOP_AFTER_P2 = 1 << 10, /* debugging (with UNFUSED): stop after the block mixing */
   MHLA_FLAG_ONLY_P3 = 1 << 11,       /* debugging (with UNFUSED): run only the readout on a caller-filled workspace */

@@ -18,6 +18,7 @@ FLAG_ONLY_P3 = 1 << 11
 FLAG_ONLY_P2 = 1 << 12
 FLAG_TWO_LAUNCH = 1 << 13
 FLAG_WS_PERSISTENT = 1 << 14
+FLAG_NO_SMALLN = 1 << 15
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",

@@ -510,7 +510,7 @@ inline int causal_launch(CausalParams& P, const CausalPlan& pl, int unfused, int
   constexpr int NVH = DV > 128 ? DV / 128 : 1;
   const long long n1 = pl.ns, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = (long long)pl.ns * NVH;
   if (unfused) {
-    for (int mode = 1; mode <= 3; ++mode) {
+    for (int mode = 1; mode <= (unfused >= 2 ? unfused - 1 : 3); ++mode) {   // unfused = 2 / 3: stop after phase 1 / 2 (timing)
       P.mode = mode;
       const long long items = (long long)pl.Gs * (mode == 1 ? n1 : (mode == 2 ? n2 : n3));
       kern<<<(int)(items < num_sms ? items : num_sms), kCausalThreads, kSmemAlloc, stream>>>(P);

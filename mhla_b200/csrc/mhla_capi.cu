@@ -14,6 +14,7 @@
 #include "../../include/mhla_b200.h"
 #include "blockmix_kernel.cuh"
 #include "causal_kernel.cuh"
+#include "smalln_kernel.cuh"
 
 namespace {
 
@@ -259,7 +260,7 @@ unsigned long long* g_prof_buffer = nullptr;   // debug: per-CTA role counters (
 constexpr int kMaxDevices = 64;
 struct DeviceState {
   int sms = 0;          // 0: not queried yet; < 0: not an sm_100 device
-  bool attr64 = false, attr128 = false;
+  bool attr64 = false, attr128 = false, attr_smalln = false;
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -278,6 +279,73 @@ int device_state(DeviceState** out) {
   }
   if (st.sms < 0) return MHLA_ERR_NO_DEVICE;
   *out = &st;
+  return MHLA_OK;
+}
+
+struct SmallNCacheEntry {
+  mhla_blockmix_desc key;
+  mhla::SmallNParams params;
+};
+std::vector<SmallNCacheEntry> g_smalln_cache;
+
+// Short sequences (DiT / ViT): the whole (b,h) unit fits one CTA - see smalln_kernel.cuh.
+bool smalln_eligible(const mhla_blockmix_desc* d) {
+  if (d->D != 64 || d->M > mhla::kSnMaxM || (long long)d->M * d->w > mhla::kSnRows) return false;
+  if (d->q_rope.ptr || d->k_rope.ptr || d->out_rms_weight) return false;
+  if (d->flags & (MHLA_FLAG_NO_SMALLN | MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH | MHLA_FLAG_FUSED | MHLA_FLAG_STOP_AFTER_P1 |
+                  MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2))
+    return false;
+  return true;
+}
+
+int launch_smalln(const mhla_blockmix_desc* d, DeviceState* dst, cudaStream_t stream) {
+  mhla::SmallNParams P;
+  {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    bool hit = false;
+    for (auto& e : g_smalln_cache)
+      if (std::memcmp(&e.key, d, sizeof(*d)) == 0) { P = e.params; hit = true; break; }
+    if (!hit) {
+      std::memset(&P, 0, sizeof P);
+      const mhla_tensor5* ts[4] = {&d->q, &d->k, &d->v, &d->out};
+      CUtensorMap* maps[4] = {&P.tmQ, &P.tmK, &P.tmV, &P.tmO};
+      for (int i = 0; i < 4; ++i) {
+        MapSpec s = spec_t5(*ts[i], d, d->w);
+        s.box[2] = (uint32_t)d->M;               // one box = all blocks of one (b,h) unit, rows in (block, token) order
+        if (!encode_map(maps[i], s)) return MHLA_ERR_CUDA;
+      }
+      P.mix = d->mix; P.mix_ld = d->mix_ld;
+      P.G = d->B * d->H; P.H = d->H; P.M = d->M; P.w = d->w; P.N = d->M * d->w;
+      P.normalize = (d->flags & MHLA_FLAG_NORMALIZE) ? 1 : 0;
+      P.is_fp16 = d->dtype == MHLA_FP16;
+      P.eps = d->eps;
+      if (g_smalln_cache.size() >= 32) g_smalln_cache.erase(g_smalln_cache.begin());
+      SmallNCacheEntry e;
+      std::memcpy(&e.key, d, sizeof(*d));
+      e.params = P;
+      g_smalln_cache.push_back(e);
+    }
+    if (!dst->attr_smalln) {
+      if (!cuda_ok(cudaFuncSetAttribute(mhla::smalln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSnSmemAlloc),
+                   "cudaFuncSetAttribute(smalln)"))
+        return MHLA_ERR_CUDA;
+      dst->attr_smalln = true;
+    }
+  }
+  P.prof = g_prof_buffer;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(P.G < dst->sms ? P.G : dst->sms);
+  cfg.blockDim = dim3(mhla::kSnThreads);
+  cfg.dynamicSmemBytes = mhla::kSnSmemAlloc;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  if (!cuda_ok(cudaLaunchKernelEx(&cfg, mhla::smalln_kernel, P), "cudaLaunchKernelEx(smalln)")) return MHLA_ERR_CUDA;
+  if (!cuda_ok(cudaGetLastError(), "kernel launch")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
   return MHLA_OK;
 }
 
@@ -324,8 +392,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (rc != MHLA_OK) return rc;
   if (!d->q.ptr || !d->k.ptr || !d->v.ptr || !d->out.ptr || !d->mix) return MHLA_ERR_INVALID_ARGUMENT;
   if ((d->q_rope.ptr == nullptr) != (d->k_rope.ptr == nullptr)) return MHLA_ERR_INVALID_ARGUMENT;
-  if (!d->workspace || d->workspace_bytes < pl.total) return MHLA_ERR_WORKSPACE;
-  if ((reinterpret_cast<uintptr_t>(d->workspace) & 1023) != 0) return MHLA_ERR_ALIGNMENT;
+  const bool small = smalln_eligible(d);      // short sequences need no workspace
+  if (!small && (!d->workspace || d->workspace_bytes < pl.total)) return MHLA_ERR_WORKSPACE;
+  if (!small && (reinterpret_cast<uintptr_t>(d->workspace) & 1023) != 0) return MHLA_ERR_ALIGNMENT;
   if (!t5_ok(d->q) || !t5_ok(d->k) || !t5_ok(d->v) || !t5_ok(d->out)) return MHLA_ERR_ALIGNMENT;
   if (d->q_rope.ptr && (!t5_ok(d->q_rope) || !t5_ok(d->k_rope))) return MHLA_ERR_ALIGNMENT;
   if (d->mix_ld < d->M) return MHLA_ERR_INVALID_ARGUMENT;
@@ -334,6 +403,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   rc = device_state(&dst);
   if (rc != MHLA_OK) return rc;
   const int num_sms = dst->sms;
+  if (small) return launch_smalln(d, dst, stream);
 
   mhla::BlockmixParams P;
   {
@@ -566,6 +636,8 @@ int mhla_fwd_causal(const mhla_causal_desc* d, void* stream_) {
   int unfused = (long long)pl.G * pl.n >= 512 ? 1 : 0;
   if (d->flags & MHLA_FLAG_UNFUSED) unfused = 1;
   if (d->flags & MHLA_FLAG_FUSED) unfused = 0;
+  if (d->flags & MHLA_FLAG_STOP_AFTER_P1) unfused = 2;   // debugging / phase timing: summaries only
+  if (d->flags & MHLA_FLAG_STOP_AFTER_P2) unfused = 3;   // ... summaries + mixing
   rc = MHLA_ERR_UNSUPPORTED_SHAPE;
 #define MHLA_CAUSAL_CASE(KK, VV) \
   if (d->K == KK && d->V == VV) rc = mhla::causal_launch<KK, VV>(P, pl, unfused, num_sms, stream, &launches);

@@ -112,7 +112,8 @@ def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
 def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                   out: Optional[torch.Tensor] = None, fused: bool = True, unfused: Optional[bool] = None,
                   three_launch: bool = False, two_launch: bool = False, force_fused: bool = False, debug_flags: int = 0,
-                  out_rms_weight: Optional[torch.Tensor] = None, out_rms_eps: float = 1e-6) -> torch.Tensor:
+                  out_rms_weight: Optional[torch.Tensor] = None, out_rms_eps: float = 1e-6,
+                  no_smalln: bool = False) -> torch.Tensor:
     """Non-causal block-mixed MHLA forward on block-major tensors (no autograd graph).
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
@@ -122,6 +123,8 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     q_rope, k_rope : roped copies for the numerator (variant B); q, k then only feed the normaliser.
     out_rms_weight : optional [D] weight of a per-(token, head) RMSNorm fused into the readout epilogue
               (out = o * rsqrt(mean_d(o^2) + out_rms_eps) * weight; MHLA_Video_Uni's g_norm, mhla_utils.py:360-362).
+    no_smalln : units of at most 256 tokens (M*w <= 256, D = 64, M <= 64: DiT / ViT) normally take the short-sequence
+              kernel (whole unit on chip, no workspace, csrc/smalln_kernel.cuh); True forces the general kernel.
     fused   : (default) one persistent kernel: items are scheduled at run time, cross-CTA dependencies go through
               per-group counters.  ``three_launch`` / ``unfused=True`` run the phases as three PDL-chained launches of
               the same kernel (an independent cross-check), ``two_launch`` as summaries+mixing followed by the readout.
@@ -168,7 +171,8 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         three_launch = bool(unfused)
     if two_launch or not fused:      # (the two-launch variant of round 1 is gone: it now means phase-by-phase launches)
         three_launch = True
-    flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else 0) | int(debug_flags))
+    flags = ((_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else 0) | int(debug_flags) |
+             (_capi.FLAG_NO_SMALLN if no_smalln else 0))
     single = not (three_launch or debug_flags)
     if single:
         flags |= _capi.FLAG_WS_PERSISTENT | (_capi.FLAG_FUSED if force_fused else 0)
@@ -211,10 +215,8 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     else:
         with torch.cuda.device(q.device):
             _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
-    # keep the operands alive until the stream has consumed them
-    for t in (q5, k5, v5, qr5, kr5, mix2, rms_w) + (() if single else (ws,)):
-        if t is not None:
-            t.record_stream(stream)
+    # (operands and temporaries belong to the current stream, like those of any other torch op: the caching allocator's
+    #  stream-ordered reuse keeps them valid for the enqueued kernel - no record_stream traffic per call)
     res = o5 if out is None else out
     if out is None:
         if D_in != D:
@@ -301,7 +303,7 @@ def mhla_causal(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
 
 
 def _causal_fwd(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[float] = None,
-                unfused: Optional[bool] = None) -> torch.Tensor:
+                unfused: Optional[bool] = None, debug_flags: int = 0) -> torch.Tensor:
     """Causal chunked MHLA forward; q,k [B,T,H,K], v [B,T,H,V] -> o [B,T,H,V] in q.dtype.
 
     T is zero-padded to a multiple of the chunk exactly as the reference does (naive.py:46-51); the pad is a host-side
@@ -336,7 +338,8 @@ def _causal_fwd(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
     d = _capi.CausalDesc()
     d.B, d.T, d.H, d.K, d.V = B, T, H, K, V
     # unfused: None = let the library choose (three launches for large batches), True / False force either structure
-    d.chunk, d.dtype, d.flags = chunk_size, _DT[cdtype], (0 if unfused is None else (_capi.FLAG_UNFUSED if unfused else _capi.FLAG_FUSED))
+    d.chunk, d.dtype = chunk_size, _DT[cdtype]
+    d.flags = (0 if unfused is None else (_capi.FLAG_UNFUSED if unfused else _capi.FLAG_FUSED)) | int(debug_flags)
     d.scale = float(K_in ** -0.5 if scale is None else scale)
     d.q, d.k, d.v, d.out = _t4(q4), _t4(k4), _t4(v4), _t4(o4)
     d.mm, d.mm_ld, d.L = mm.data_ptr(), mm.stride(0), Lm
@@ -348,8 +351,6 @@ def _causal_fwd(q, k, v, mixing_matrix, chunk_size: int = 64, scale: Optional[fl
     d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
     with torch.cuda.device(q.device):
         _capi.check(L.mhla_fwd_causal(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_causal")
-    for t in (q4, k4, v4, mm, ws):
-        t.record_stream(torch.cuda.current_stream())
     if pad or V != V_in:
         o4 = o4[:, :T_in, :, :V_in]
     return o4 if in_dtype == cdtype else o4.to(in_dtype)

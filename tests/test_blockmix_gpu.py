@@ -55,14 +55,15 @@ def _run(q, k, v, W, qr=None, kr=None, normalize=True, eps=1e-6, **kw):
     (1, 2, 5, 100, 64, True, False, torch.float16),         # ragged w, fp16
     (1, 1, 1, 256, 64, True, False, torch.bfloat16),        # single block
 ])
-@pytest.mark.parametrize("path", ["fused", "three_launch"])
+@pytest.mark.parametrize("path", ["default", "no_smalln", "three_launch"])
 def test_blockmix_vs_oracle(B, H, M, w, D, normalize, rope, dtype, path):
-    """Both launch structures of the C ABI (the default single fused kernel and the three PDL-chained phase launches)
-    against the oracle."""
+    """Every launch structure of the C ABI against the oracle: the default (the short-sequence kernel for units of at most
+    256 tokens, else the single fused kernel), the fused general kernel forced (no_smalln) and the three PDL-chained phase
+    launches."""
     q, k, v, qr, kr = _inputs(B, H, M, w, D, dtype, rope=rope)
     g = torch.Generator().manual_seed(1)
     W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
-    out = _run(q, k, v, W, qr, kr, normalize=normalize, **({} if path == "fused" else {path: True}))
+    out = _run(q, k, v, W, qr, kr, normalize=normalize, **({} if path == "default" else {path: True}))
     ref = oracle.blockmix_fwd(q, k, v, W, normalize=normalize, q_rope=qr, k_rope=kr)
     _check(ref, out, dtype)
 
@@ -180,6 +181,38 @@ def test_blockmix_fused_output_rmsnorm(B, H, M, w, D, normalize, rope):
     _check(ref, out, torch.bfloat16)
 
 
+@pytest.mark.parametrize("B,H,M,w,normalize,dtype", [
+    (2, 6, 16, 16, True, torch.bfloat16),      # DiT-S/2 256x256 (BASELINE cfg2)
+    (3, 2, 4, 49, True, torch.bfloat16),       # the modules' default block_size = 49 (N = 196: ragged second row tile)
+    (1, 3, 3, 7, True, torch.bfloat16),        # N = 21: one partial row tile
+    (2, 2, 64, 4, True, torch.bfloat16),       # M = 64 blocks of 4 tokens
+    (1, 2, 16, 8, False, torch.bfloat16),      # N = 128: exactly one row tile, no normaliser
+    (1, 2, 37, 1, True, torch.bfloat16),       # one token per block
+    (2, 2, 1, 256, True, torch.bfloat16),      # a single block of 256 tokens
+    (2, 3, 4, 64, True, torch.float16),        # fp16
+    (150, 6, 16, 16, True, torch.bfloat16),    # 900 units: several units per CTA (ring reuse, barrier phases)
+])
+def test_smalln_kernel_vs_oracle_and_general_kernel(B, H, M, w, normalize, dtype):
+    """The short-sequence kernel (csrc/smalln_kernel.cuh) against the oracle, and against the general kernel on the
+    same inputs (two independent formulations of mhla.py:262-268)."""
+    import mhla_b200
+    D = 64
+    q, k, v, _, _ = _inputs(B, H, M, w, D, dtype, seed=41)
+    g = torch.Generator().manual_seed(42)
+    W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
+    out = _run(q, k, v, W, normalize=normalize)
+    assert mhla_b200.last_launch_count() == 1
+    sel = slice(0, min(B, 3))
+    _check(oracle.blockmix_fwd(q[sel], k[sel], v[sel], W, normalize=normalize), out[sel], dtype)
+    _check(oracle.blockmix_fwd(q[-1:], k[-1:], v[-1:], W, normalize=normalize), out[-1:], dtype)
+    gen = _run(q, k, v, W, normalize=normalize, no_smalln=True)
+    assert oracle.err_ratio(gen.float().cpu(), out.float().cpu()) < 6e-3
+    again = _run(q, k, v, W, normalize=normalize)
+    assert torch.equal(out, again)                       # deterministic
+    if B > 1:
+        assert torch.equal(_run(q[1:], k[1:], v[1:], W, normalize=normalize), out[1:])   # unit-shard equivalence
+
+
 def test_blockmix_padded_head_dim():
     """DiT-XL heads (1152 / 16 = 72 channels, mhla_dit/models.py:478-549) run zero-padded to 128 in the shim."""
     B, H, M, w, D = 1, 2, 16, 16, 72
@@ -212,3 +245,41 @@ def test_errors_are_loud():
     q = torch.zeros(1, 1, 2, 16, 32, dtype=torch.bfloat16, device="cuda")
     with pytest.raises(RuntimeError):
         mhla_b200.mhla(q.cpu(), q.cpu(), q.cpu(), torch.eye(2))       # CPU tensors: no fallback
+
+
+def test_cuda_graph_capture_of_a_dit_stack():
+    """28 DiT-S/2 layers x batch 2 (BASELINE cfg2) captured into ONE CUDA graph: the operator only enqueues on the current
+    stream (no allocation of its own after warm-up, no sync), so a whole sampler step can be replayed without the Python /
+    ctypes enqueue cost.  The replayed result must equal the eagerly computed one bit for bit."""
+    import mhla_b200
+    B, H, M, w, D, layers = 2, 6, 16, 16, 64, 28
+    q, k, v, _, _ = _inputs(B, H, M, w, D, torch.bfloat16, seed=51)
+    q, k, v = q.cuda(), k.cuda(), v.cuda()
+    Ws = [(torch.rand(M, M, generator=torch.Generator().manual_seed(60 + i)) / M).cuda() for i in range(layers)]
+    outs = [torch.empty_like(q) for _ in range(layers)]
+    eager = [mhla_b200.mhla(q, k, v, Ws[i]).clone() for i in range(layers)]     # also warms the descriptor caches
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(layers):
+            mhla_b200.mhla(q, k, v, Ws[i], out=outs[i])
+    for o in outs:
+        o.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for i in range(layers):
+        assert torch.equal(outs[i], eager[i])
+    # the general kernel (persistent self-cleaning workspace) is capturable as well
+    qg, kg, vg, _, _ = _inputs(1, 2, 8, 128, 64, torch.bfloat16, seed=52)
+    qg, kg, vg = qg.cuda(), kg.cuda(), vg.cuda()
+    Wg = (torch.rand(8, 8) / 8).cuda()
+    ref = mhla_b200.mhla(qg, kg, vg, Wg).clone()
+    og = torch.empty_like(qg)
+    torch.cuda.synchronize()
+    g2 = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g2):
+        for _ in range(3):
+            mhla_b200.mhla(qg, kg, vg, Wg, out=og)
+    g2.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(og, ref)

@@ -1,0 +1,70 @@
+"""NCCL tests of the (b,h)-unit sharding on real GPUs (`-m gpu`, needs >= 2 devices; the driver's single-GPU run skips
+them - `gpurun --gpus 2 -- python -m pytest tests/test_sharded_nccl.py -m gpu` is how the log in profiles/ was made).
+One process per GPU, torch.distributed over NCCL; every rank runs the single-GPU kernel on its slice of the units and ONE
+all_gather_into_tensor reassembles the outputs.  The result must be BITWISE equal to the single-GPU run."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, shape, normalize, q_out):
+    import torch.distributed as dist
+    import mhla_b200
+    from mhla_b200.sharded import mhla_sharded, unit_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        G, M, w, D = shape
+        g = torch.Generator().manual_seed(0)
+        q = (torch.relu(torch.randn(G, M, w, D, generator=g)) + 1e-6).bfloat16().to(dev)
+        k = (torch.relu(torch.randn(G, M, w, D, generator=g)) + 1e-6).bfloat16().to(dev)
+        v = torch.randn(G, M, w, D, generator=g).bfloat16().to(dev)
+        W = (torch.rand(M, M, generator=g) / M).to(dev)
+        full = mhla_b200.mhla(q, k, v, W, normalize=normalize)                      # single-GPU reference on this rank
+        lo, hi = unit_range(G, world, rank)
+        a = mhla_sharded(q, k, v, W, gather=True, inputs="full", normalize=normalize)
+        b = mhla_sharded(q[lo:hi], k[lo:hi], v[lo:hi], W, gather=True, inputs="local", total_units=G, normalize=normalize)
+        c = mhla_sharded(q[lo:hi], k[lo:hi], v[lo:hi], W, gather=False, inputs="local", total_units=G, normalize=normalize)
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(a, full) and torch.equal(b, full) and torch.equal(c, full[lo:hi]))
+        q_out.put((rank, ok, tuple(a.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, shape, normalize):
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, shape, normalize, q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    results = sorted(q_out.get(timeout=10) for _ in range(world))
+    assert all(ok for _, ok, _ in results), results
+    assert all(s[0] == shape[0] for _, _, s in results)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("shape,normalize", [((32, 32, 256, 64), True), ((12, 20, 210, 128), False), ((5, 16, 16, 64), True)])
+def test_sharded_nccl_bitwise_equals_single_gpu(world, shape, normalize):
+    """BASELINE's 32 units (at N = 8192), Wan's 12 heads (uneven over 8 ranks: padded all-gather) and a short-sequence
+    case with fewer units than ranks."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    _run(world, shape, normalize)
