@@ -103,6 +103,10 @@ typedef struct mhla_blockmix_desc {
 } mhla_blockmix_desc;
 
 size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);
+/* 1 when mhla_fwd_blockmix(desc) uses the workspace; 0 for shapes that take the short-sequence kernel (M*w <= 256 tokens
+ * per (b,h) unit, D = 64, M <= 64, no rope / fused output norm): workspace may then be NULL.  Pointers in desc are ignored
+ * except that q_rope / k_rope / out_rms_weight must be NULL or non-NULL as in the later call. */
+int mhla_blockmix_needs_workspace(const mhla_blockmix_desc* desc);
 /* White-box view of the workspace for tests: out[0..7] = byte offsets of S, S~, den, padded mix, counters,
  * then ncols (floats per S row: D*D summaries followed by wpad n_loc entries), wpad, padded mix pitch. */
 int mhla_blockmix_workspace_layout(const mhla_blockmix_desc* desc, size_t out[8]);

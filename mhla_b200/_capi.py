@@ -22,7 +22,7 @@ FLAG_NO_SMALLN = 1 << 15
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
-    "mhla_blockmix_workspace_bytes", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
 ]
 
 
@@ -78,6 +78,9 @@ def lib() -> C.CDLL:
         L.mhla_last_launch_count.restype = C.c_int
         L.mhla_blockmix_workspace_bytes.restype = C.c_size_t
         L.mhla_blockmix_workspace_bytes.argtypes = [C.POINTER(BlockmixDesc)]
+        if hasattr(L, "mhla_blockmix_needs_workspace"):     # (absent in older A/B builds loaded through MHLA_B200_LIB)
+            L.mhla_blockmix_needs_workspace.restype = C.c_int
+            L.mhla_blockmix_needs_workspace.argtypes = [C.POINTER(BlockmixDesc)]
         L.mhla_blockmix_workspace_layout.restype = C.c_int
         L.mhla_blockmix_workspace_layout.argtypes = [C.POINTER(BlockmixDesc), C.POINTER(C.c_size_t * 8)]
         L.mhla_fwd_blockmix.restype = C.c_int

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmhla_b200.so")
 SOURCES = ["mhla_capi.cu"]
-HEADERS = ["ptx.cuh", "blockmix_kernel.cuh", "causal_kernel.cuh", os.path.join("..", "..", "include", "mhla_b200.h")]
+HEADERS = ["ptx.cuh", "blockmix_kernel.cuh", "causal_kernel.cuh", "smalln_kernel.cuh", os.path.join("..", "..", "include", "mhla_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "--use_fast_math",
@@ -36,6 +36,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+LIB_DIAG = os.path.join(HERE, "libmhla_b200_diag.so")
+
+
+def build_diag() -> str:
+    """The diagnostics build (-DMHLA_DIAG: time-bounded waits that record a stall in host-mapped memory before trapping);
+    tools/stress.py loads it through MHLA_B200_LIB.  Not used by the product path."""
+    cmd = [_nvcc(), *NVCC_FLAGS, "-DMHLA_DIAG", "-o", LIB_DIAG, *[os.path.join(CSRC, s) for s in SOURCES]]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError(f"nvcc failed:\n{proc.stdout}\n{proc.stderr}")
+    return LIB_DIAG
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -53,3 +66,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    if "--diag" in sys.argv:
+        print(build_diag())

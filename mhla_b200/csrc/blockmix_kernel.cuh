@@ -13,16 +13,10 @@
 //   P3 (g, i)        O_i = (Q_i S~_i) / den_i
 // Items are handed out through global tickets and the ORDER in which a CTA runs them is decided at run time by a
 // scheduler warp: a dependent item (P2 needs all P1 of its group, P3 all P2) is only enqueued once its group's arrival
-// counter in global memory (release/acquire) says it is ready, so no role ever blocks on a dependency.  Order of
-// preference: ready P2 items, then P1 items, the readout (P3) last - the kernel streams K,V,Q once for the summaries and
-// Q once more for the readout, and the latency of the P1 -> P2 -> P3 chain of a group never sits on the critical path.
-// The scheduler feeds the other roles through a small FIFO in shared memory.
-//
-// Every result (S, S~, den, O) leaves shared memory by TMA store (the LSU store path stalls for thousands of cycles
-// while the memory system is saturated by the streaming loads: a P2 epilogue took 8.4k cycles with 16-byte global
-// stores, profiles/r02_notes.md).  A workspace-producing item is published LAZILY: the thread that issued its TMA stores
-// waits for their completion only when it next looks at the item FIFO (by then they have long landed), then bumps a
-// shared-memory counter that the signal warp turns into the group's arrival counter (red.release.gpu).
+// counter in global memory (release/acquire) says it is ready, so no role ever blocks on a dependency.  Default
+// policy: ready P2 items first, then P1, the readout (P3) last; `policy 0` puts ready P3 items before new P1 items
+// within a window of groups (keeps Q in L2, but stalls on the P1 -> P2 -> P3 latency chain).  The scheduler feeds the
+// other roles through a small FIFO in shared memory; all CTAs are co-resident (grid <= #SMs, 1 CTA/SM).
 #pragma once
 #include <cuda.h>
 #include <type_traits>
@@ -35,8 +29,8 @@ constexpr int kNumStages = 5;            // default ring depth (fused kernel, P2
 constexpr int kMaxStages = 6;            // P1-only launches with D = 64 trade staging for a sixth stage
 constexpr int kStagingBytes = 16384;  // one staging slot: [128 rows][128 B] swizzle-128B tile
 constexpr int kStagingPerWg = 2 * kStagingBytes;   // each epilogue warpgroup owns two slots = one hand-off of <= 2 chunks
-constexpr int kThreads = 384;         // warp 0: TMA producer, 1: MMA issuer, 2: scheduler (+TMEM alloc),
-                                      // 3: signal, 4-7: epilogue warpgroup 0 (even items), 8-11: warpgroup 1 (odd items)
+constexpr int kThreads = 384;         // warp 0: TMA producer, 1: MMA issuer, 2: dependency poller (+TMEM alloc),
+                                      // 3: store/signal, 4-7: epilogue warpgroup 0 (even items), 8-11: warpgroup 1 (odd items)
 constexpr int kEpiThreads = 128;
 constexpr int kTmemCols = 512;
 constexpr int kAccCols = 256;         // two accumulator buffers of 256 columns
@@ -79,23 +73,25 @@ struct alignas(64) BlockmixParams {
   int n2_rows, n2_cols, n2_scols;           // P2 tile grid; first n2_scols column tiles are S columns
   int kslabs;                               // ceil(M / 64)
   int normalize, ropenorm, is_fp16;
-  int mode;                                 // 0: fused; 1/2/3: only that phase (phase-by-phase launches)
+  int mode;                                 // 0: fused; 1/2/3: only that phase (unfused debugging path)
+  int window;                               // fused mode: P1 may run this many groups ahead of the CTA's next P3 item
   int run_ahead;                            // fused mode: items the scheduler may enqueue ahead of the producer
+  int np2;                                  // fused mode: CTAs [0, np2) run only P2 items (0: every CTA owns P2 items too)
   float eps;
   unsigned long long* prof;                 // optional [gridDim][16] cycle counters (debug, tools/prof_roles.py)
-  int mix_hi_only;                          // bf16: S columns of the block mixing take the 8-bit hi plane only
+  int mix_hi_only;                          // bf16: S columns of the block mixing take the 8-bit hi plane only (MHLA_FLAG_FAST_MIX)
   int slots_per_wg;                         // staging slots per epilogue warpgroup (2, or 1 to buy another ring stage)
   int ring_stages, slot_bytes;              // smem carve-up of this launch (see kernel prologue)
+  int q_hint;                               // 1: evict-first on the normaliser's Q loads when the readout comes much later
   int o_hint;                               // 1: evict-first L2 hint on the output stores
-  int ws_hint;                              // 1: evict-last on the S~ / den stores, evict-first when they are consumed
-  int p2_tma;                               // 1: S~ / den tiles leave by TMA store (lazy publication); 0: 16-byte global stores
-  int q_keep;                               // fused mode: the normaliser's Q tiles of the last q_keep groups are loaded
-                                            // evict-last and the readout walks the groups backwards (they are still in L2)
+  int policy;                               // mode 0: 0 = ready P3 items before new P1 items (window), 1 = P3 items last
+  int reverse3;                             // mode 3: walk the groups backwards
+  int pf_dist;                              // L2 prefetch distance of the producer, in own streaming items (0: off)
   int trace_cta;                            // debug: CTA whose event trace is recorded
   int cnt_stride;                           // words between two dependency counters (padded to separate L2 sectors)
 };
 
-// Event trace of one CTA (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
+// Event trace of CTA 0 (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
 __device__ __forceinline__ void trace_ev(const BlockmixParams& p, int role, uint32_t item, int slot) {
   if (p.prof != nullptr && (int)blockIdx.x == p.trace_cta && item < 256)
     p.prof[(size_t)gridDim.x * 16 + ((size_t)role * 256 + item) * 4 + slot] = (unsigned long long)clock64();
@@ -126,12 +122,42 @@ struct ItemStream {
   __device__ ItemStream(const uint32_t* f, const uint32_t* pub) : fifo(f), published(pub) {}
   __device__ __forceinline__ bool ready() const { return ld_acquire_cta_shared(published) > idx; }
   // single-lane roles
-  __device__ __forceinline__ bool next(Item& it, uint32_t role) {
+  // (the product build keeps the exact round-1 polling loops: a few more integer instructions in them cost the headline
+  //  kernel 3 %, see ptx.cuh; -DMHLA_DIAG swaps in the time-bounded, record-writing variants)
+  __device__ __forceinline__ bool next(Item& it) {
+#ifdef MHLA_DIAG
     SpinGuard guard;
     while (!ready()) {
-      __nanosleep(20);   // keep the poll off the shared-memory pipe the epilogue warps of this SM sub-partition use
-      if (guard.expired()) report_stall(2, role, idx);
+      __nanosleep(20);
+      if (guard.expired()) report_stall(2, 0, idx);
     }
+#else
+    uint32_t spins = 0;
+    while (!ready()) {
+      __nanosleep(20);   // keep the poll off the shared-memory pipe the epilogue warps of this SM sub-partition use
+      if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: item stream stalled (block %d)\n", blockIdx.x); __trap(); }
+    }
+#endif
+    return take(it);
+  }
+  // whole-warp roles: one lane polls, the warp then reads the entry together
+  __device__ __forceinline__ bool next_warp(Item& it, int lane) {
+    if (lane == 0) {
+#ifdef MHLA_DIAG
+      SpinGuard guard;
+      while (!ready()) {
+        __nanosleep(32);
+        if (guard.expired()) report_stall(2, 8, idx);
+      }
+#else
+      uint32_t spins = 0;
+      while (!ready()) {
+        __nanosleep(32);
+        if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: item stream stalled (block %d)\n", blockIdx.x); __trap(); }
+      }
+#endif
+    }
+    __syncwarp();
     return take(it);
   }
   __device__ __forceinline__ bool take(Item& it) {
@@ -146,9 +172,10 @@ struct Ring {
   int stage = 0;
   uint32_t phase = 0;
   int depth = kNumStages;
+  int base = 0;     // first physical stage of this ring (stages below it hold resident data)
   __device__ Ring() {}
-  __device__ explicit Ring(int d) : depth(d) {}
-  __device__ __forceinline__ int idx() const { return stage; }
+  __device__ explicit Ring(int d, int b = 0) : depth(d - b), base(b) {}
+  __device__ __forceinline__ int idx() const { return base + stage; }
   __device__ __forceinline__ void advance(int n = 1) {
     stage += n;
     while (stage >= depth) { stage -= depth; phase ^= 1; }
@@ -157,11 +184,19 @@ struct Ring {
 };
 
 __device__ __forceinline__ void spin_until(const uint32_t* cnt, uint32_t target) {
+#ifdef MHLA_DIAG
   SpinGuard guard;
   while (ld_acquire_gpu(cnt) < target) {
     __nanosleep(64);
     if (guard.expired()) report_stall(6, target, ld_acquire_gpu(cnt));
   }
+#else
+  uint32_t spins = 0;
+  while (ld_acquire_gpu(cnt) < target) {
+    __nanosleep(64);
+    if (++spins > (1u << 24)) { printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+  }
+#endif
 }
 
 // Number of ring stages an item occupies (identical in every role).
@@ -194,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   uint32_t* q_published = tmem_slot + 1;   // items the scheduler warp (warp 2) has enqueued
   uint32_t* q_started = tmem_slot + 2;     // items the producer has picked up (throttles the scheduler's run-ahead)
-  uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished (and landed) per epilogue warpgroup
+  uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished by each epilogue warpgroup
   float* wscale_s = reinterpret_cast<float*>(tmem_slot + 5);   // self_prep: power of two the mixing matrix was divided by
   uint32_t* last_flag = tmem_slot + 6;     // self_prep: this CTA is the last one to finish
   uint32_t* fifo = reinterpret_cast<uint32_t*>(smem + kSmemFifo);
@@ -203,7 +238,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   const int lane = threadIdx.x & 31;
   const int tile_bytes = p.TW * 128;  // one [TW rows][64 x 16-bit] swizzle-128B tile
   const uint32_t fmt16 = p.is_fp16 ? 0u : 1u;
-  const bool dynamic = p.mode == 0;   // in-kernel dependencies through the per-group counters
+  // Dedicated block-mixing CTA of the fused kernel: the mixing matrix (hi | lo, one ring stage per 64-block slab) stays
+  // resident in ring stages [0, kslabs) and only the S / n_loc tiles stream through the remaining stages.
+  // in-kernel dependencies through the per-group counters: 0 = all phases, 4 = P1 + P2 only, 5 = P3 only, started by PDL
+  // while the mode-4 grid is still draining (no griddepcontrol.wait: the counters carry the dependency)
+  const bool dynamic = p.mode == 0 || p.mode == 4 || p.mode == 5;
+  const bool wres = dynamic && (int)blockIdx.x < p.np2 && p.n2_rows == 1 && p.kslabs <= 2;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
@@ -224,12 +264,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  grid_dependency_wait();   // PDL: everything above overlapped the tail of the previous kernel in the stream
+  if (p.mode != 5) grid_dependency_wait();   // PDL: everything above overlapped the tail of the previous kernel in the stream
   grid_launch_dependents(); // ... and the next kernel may start its own prologue as soon as SMs free up
   // debug timeline: [mode][cta] = {globaltimer at start of work, at end}, behind the per-CTA counters and the CTA trace
   unsigned long long* const tl = p.prof == nullptr ? nullptr
       : p.prof + (size_t)gridDim.x * 16 + 4 * 256 * 4 + ((size_t)p.mode * 148 + blockIdx.x) * 4;
-  if (tl != nullptr && threadIdx.x == 0) tl[0] = gtimer_ns();
+  if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[0] = t; }
 
   ItemStream sched(fifo, q_published);
   Item it;
@@ -237,18 +277,56 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   if (warp == 0) {
     // ============================================================ TMA producer (one lane)
     if (elect_one()) {
-      Ring r(nst);
+      Ring r(nst, wres ? p.kslabs : 0);
       const bool prof_on = p.prof != nullptr;
       long long w_empty = 0, w_dep = 0;
       const long long t_begin = clock64();
-      const unsigned long long gt_begin = gtimer_ns();
+      unsigned long long gt_begin;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_begin));
       uint32_t pitem = 0;
-      // workspace tiles are dead once consumed: let them leave L2 first (ws_hint)
-      const uint64_t ws_ld_hint = p.ws_hint ? kEvictFirst : kEvictNormal;
-      const uint64_t s_ld_hint = (p.ws_hint && p.n2_rows == 1) ? kEvictFirst : kEvictNormal;   // S is read once per row tile
+      // A dependent item is only enqueued after the scheduler lane has acquired its group's counter; the FIFO hand-off
+      // (release/acquire in shared memory) extends that to this lane, the proxy fence to the TMA loads issued below.
+      auto wait_dependency = [&]() { fence_proxy_async_all(); };
+      // Q tiles of the normaliser: worth keeping in L2 only if the readout follows within a few groups (policy 0)
+      const uint64_t q_hint = (p.mode == 0 && p.policy == 0) ? kEvictLast : (p.q_hint ? kEvictFirst : kEvictNormal);
+      // The streaming items a CTA owns are a fixed arithmetic sequence of linear block indices, so the producer can pull
+      // the tiles of the item `pf_dist` places further down its own list into L2 while it fills shared memory for the
+      // current one: the shared-memory fill then sees L2 latency instead of HBM latency, and the bytes in flight towards
+      // HBM are no longer bounded by the ring.
+      const long long n1tot_p = (long long)p.G * p.M;
+      const long long nct13_p = (dynamic && p.np2 > 0) ? (long long)gridDim.x - p.np2 : (long long)gridDim.x;
+      auto prefetch_block = [&](long long idx, bool kv, bool q_norm, bool q_read) {
+        if (p.pf_dist <= 0) return;
+        idx += (long long)p.pf_dist * nct13_p;
+        if (idx >= n1tot_p) return;
+        const int g_ = (int)(idx / p.M0), j_ = (int)(idx % p.M0);   // linear block index = real group * M0 + block
+        const int b_ = g_ / p.H, h_ = g_ % p.H;
+        for (int sub = 0; sub < p.nsub; ++sub)
+          for (int c0 = 0; c0 < D; c0 += 64) {
+            if (kv) {
+              tma_prefetch_5d(&p.tmK, c0, sub * p.TW, j_, h_, b_);
+              tma_prefetch_5d(&p.tmV, c0, sub * p.TW, j_, h_, b_);
+              if (p.ropenorm) tma_prefetch_5d(&p.tmKn, c0, sub * p.TW, j_, h_, b_);
+            }
+            if (q_norm) tma_prefetch_5d(&p.tmQn, c0, sub * p.TW, j_, h_, b_);
+            if (q_read) tma_prefetch_5d(&p.tmQr, c0, sub * p.TW, j_, h_, b_);
+          }
+      };
+      if (wres) {
+        if (p.self_prep) {   // the planes are being written by the CTAs of this very launch: wait until all have announced
+          spin_until(p.counters + (size_t)2 * p.G * p.cnt_stride + 64, gridDim.x);
+          fence_proxy_async_all();
+        }
+        for (int slab = 0; slab < p.kslabs; ++slab) {
+          uint8_t* st = ring + slab * kStageBytes;
+          mbar_arrive_expect_tx(&full[slab], 32768);
+          tma_load_3d(st, &p.tmW, &full[slab], slab * 64, 0, 0, kEvictLast);
+          tma_load_3d(st + 16384, &p.tmW, &full[slab], slab * 64, 0, 1, kEvictLast);
+        }
+      }
       while (true) {
         const long long tq0 = prof_on ? clock64() : 0;
-        const bool more = sched.next(it, 0);
+        const bool more = sched.next(it);
         if (prof_on) w_dep += clock64() - tq0;      // time spent waiting for the scheduler (nothing ready)
         if (!more) break;
         st_release_cta_shared(q_started, sched.idx);
@@ -290,9 +368,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
           if (p.normalize) {
-            // Q tiles of the normaliser: the readout reads the same tensor again much later - only the last q_keep
-            // groups (which the backwards readout visits first) are worth keeping in L2
-            const uint64_t q_hint = (dynamic && !p.ropenorm && it.g >= p.G - p.q_keep) ? kEvictLast : kEvictFirst;
             if constexpr (D == 64) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.idx() * kStageBytes;
@@ -311,29 +386,32 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               }
             }
           }
+          // (after this item's own loads: the TMA unit serves its queue in order)
+          prefetch_block((long long)it.g * p.M + it.t, true, p.normalize != 0, false);
         } else if (it.type == 2) {
-          // A dependent item is only enqueued after the scheduler lane has acquired its group's counter; the FIFO
-          // hand-off (release/acquire in shared memory) extends that to this lane, the proxy fence to the TMA loads.
-          if (dynamic) fence_proxy_async_all();
+          if (dynamic) wait_dependency();
           const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
           for (int slab = 0; slab < p.kslabs; ++slab) {
             // stage X: mix hi | mix lo, [128 i][64 j] each; stage Y: [64 j][256 cols] as 4 tiles of 64 columns
-            mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
-            uint8_t* st = ring + r.idx() * kStageBytes;
-            const bool need_lo = !(p.is_fp16 || p.mix_hi_only) || tc >= p.n2_scols;
-            mbar_arrive_expect_tx(&full[r.idx()], need_lo ? 32768 : 16384);
-            tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
-            if (need_lo) tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
-            r.advance();
+            uint8_t* st;
+            if (!wres) {
+              mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
+              st = ring + r.idx() * kStageBytes;
+              const bool need_lo = !(p.is_fp16 || p.mix_hi_only) || tc >= p.n2_scols;
+              mbar_arrive_expect_tx(&full[r.idx()], need_lo ? 32768 : 16384);
+              tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
+              if (need_lo) tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
+              r.advance();
+            }
             mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
             st = ring + r.idx() * kStageBytes;
             mbar_arrive_expect_tx(&full[r.idx()], 32768);
             for (int n4 = 0; n4 < 4; ++n4)
-              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.idx()], tc * 256 + n4 * 64, slab * 64, it.g, s_ld_hint);
+              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.idx()], tc * 256 + n4 * 64, slab * 64, it.g, kEvictNormal);
             r.advance();
           }
         } else {
-          if (dynamic) fence_proxy_async_all();
+          if (dynamic) wait_dependency();
           const int i = it.t % p.M0;                 // block inside its real group (tensor coordinate)
           const int irow = it.g * p.M + it.t;        // row of the block in the S~ workspace
           const CUtensorMap* tq = &p.tmQr;
@@ -343,15 +421,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               uint8_t* st = ring + r.idx() * kStageBytes;
               mbar_arrive_expect_tx(&full[r.idx()], tile_bytes + (sub == 0 ? 8192 : 0));
               tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
-              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, irow, ws_ld_hint);
+              if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, irow, kEvictFirst);
               r.advance();
             }
           } else {
             mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
             uint8_t* st = ring + r.idx() * kStageBytes;
             mbar_arrive_expect_tx(&full[r.idx()], 32768);
-            tma_load_3d(st, &p.tmStld, &full[r.idx()], 0, 0, irow, ws_ld_hint);
-            tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 64, 0, irow, ws_ld_hint);
+            tma_load_3d(st, &p.tmStld, &full[r.idx()], 0, 0, irow, kEvictFirst);
+            tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 64, 0, irow, kEvictFirst);
             r.advance();
             for (int sub = 0; sub < p.nsub; ++sub) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
@@ -362,6 +440,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             }
           }
+          // the readout's Q tile has not been read before unless the normaliser pulled the same tensor through L2
+          if (!p.normalize || p.ropenorm || p.mode != 0) prefetch_block((long long)it.g * p.M + it.t, false, false, true);
         }
         trace_ev(p, 0, pitem, 1);
         ++pitem;
@@ -370,13 +450,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
         pr[0] = (unsigned long long)w_empty; pr[1] = (unsigned long long)w_dep;
         pr[2] = (unsigned long long)(clock64() - t_begin);
-        pr[14] = gtimer_ns() - gt_begin;   // nanoseconds: pr[2] / pr[14] = SM clock in GHz
+        unsigned long long gt_end;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_end));
+        pr[14] = gt_end - gt_begin;   // nanoseconds: pr[2] / pr[14] = SM clock in GHz
       }
     }
   } else if (warp == 1) {
     // ============================================================ tcgen05 issuer (one lane)
     if (elect_one()) {
-      Ring r(nst);
+      Ring r(nst, wres ? p.kslabs : 0);
       uint32_t nitem = 0;
       const bool prof_on = p.prof != nullptr;
       long long w_full = 0, w_tempty = 0;
@@ -395,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint64_t tmpl_mn8k = make_smem_desc(0, 8192, 1024, kSwizzle128);     // MN-major, tiles 8 KB apart (P2 B operand)
       const uint64_t tmpl_k = make_smem_desc(0, 0, 1024, kSwizzle128);           // K-major
       auto dsc = [](uint64_t tmpl, uint32_t saddr) -> uint64_t { return tmpl | (uint64_t)((saddr & 0x3FFFF) >> 4); };
-      while (sched.next(it, 1)) {
+      while (sched.next(it)) {
         const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
         const uint32_t acc = tmem_base + ab * kAccCols;
         trace_ev(p, 1, nitem, 0);
@@ -472,10 +554,17 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           mbar_arrive(&tfull[ab]);
         } else if (it.type == 2) {
           for (int slab = 0; slab < p.kslabs; ++slab) {
-            mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
-            const uint32_t a_addr = ring_addr + r.idx() * kStageBytes;
-            const int sa = r.idx();
-            r.advance();
+            uint32_t a_addr;
+            int sa = -1;
+            if (wres) {
+              if (nitem == 0) mbar_wait_prof(&full[slab], 0, prof_on, w_full);   // resident mixing matrix: loaded once
+              a_addr = ring_addr + slab * kStageBytes;
+            } else {
+              mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
+              a_addr = ring_addr + r.idx() * kStageBytes;
+              sa = r.idx();
+              r.advance();
+            }
             mbar_wait_prof(&full[r.idx()], r.phase, prof_on, w_full);
             tc_fence_after();
             const uint64_t dhi0 = dsc(tmpl_k, a_addr), dlo0 = dsc(tmpl_k, a_addr + 16384);   // K-major: 32 B per k-step
@@ -494,7 +583,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
             }
-            mma_commit(&empty[sa]);
+            if (sa >= 0) mma_commit(&empty[sa]);
             mma_commit(&empty[r.idx()]);
             r.advance();
           }
@@ -539,17 +628,32 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // faster simply takes more of them, so all CTAs finish together); the scheduler keeps at most one claimed item per
     // kind and decides which of them to run next:
     //   1. the claimed P2 item, if every P1 item of its group has signalled     (unblocks the whole group's readout)
-    //   2. the claimed P1 item
-    //   3. the claimed P3 item, if every P2 item of its group has signalled     (the readout comes last)
+    //   2. the claimed P3 item, if every P2 item of its group has signalled
+    //   3. the claimed P1 item, unless it is `window` or more groups ahead of the claimed P3 item (bounds the L2 footprint)
     // An item enters the FIFO only when it is ready, so no other role ever waits on a dependency and the in-order
     // pipeline behind the FIFO cannot deadlock: tickets are claimed in group order, P1 items never depend on anything,
-    // and a claimed-but-not-ready item never blocks the other kinds.
+    // and a claimed-but-not-ready item never blocks the other kinds except through the window - whose P1 items all
+    // belong to later groups than the P3 item that is being waited for.
     if (elect_one()) {
       const long long n1tot = (long long)p.G * p.M;
       const int n2per = p.n2_rows * p.n2_cols;
       const long long n2tot = (long long)p.G * n2per;
-      bool has1 = p.mode == 0 || p.mode == 1, has2 = p.mode == 0 || p.mode == 2, has3 = p.mode == 0 || p.mode == 3;
-      const bool dep = dynamic;    // P2 items wait for their group's P1 counter, P3 items for its P2 counter
+      const bool dyn = dynamic;
+      // The block mixing of a group sits on the critical path between its summaries and its readout; with np2 > 0 a few
+      // CTAs do nothing else, so a P2 item never queues behind streaming items in an in-order pipeline.
+      const int np2 = dyn ? p.np2 : 0;
+      bool has1 = true, has2 = true, has3 = true;
+      const bool dedicated = np2 > 0 && (int)blockIdx.x < np2;
+      if (np2 > 0) {
+        if (dedicated) has1 = false; else has2 = false;   // (a dedicated CTA joins the readout once the mixing is done)
+      }
+      if (p.mode == 1) { has2 = false; has3 = false; }
+      if (p.mode == 2) { has1 = false; has3 = false; }
+      if (p.mode == 3 || p.mode == 5) { has1 = false; has2 = false; }
+      if (p.mode == 4) has3 = false;
+      const bool dep2 = p.mode == 0 || p.mode == 4;   // P2 items wait for their group's P1 counter
+      const bool dep3 = p.mode == 0 || p.mode == 5;   // P3 items wait for their group's P2 counter
+      const bool rev3 = (p.mode == 3 || p.mode == 5) && p.reverse3;   // stand-alone readout: last groups first
       unsigned long long* const tickets = reinterpret_cast<unsigned long long*>(p.counters + (size_t)2 * p.G * p.cnt_stride);
       // (a short queue also keeps the tickets balanced: a CTA never hoards items it will only reach much later)
       const uint32_t run_ahead = (uint32_t)p.run_ahead;
@@ -557,70 +661,111 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       int ready1_g = -1, ready2_g = -1;   // groups already known to have all P1 / all P2 items done
       bool w_ok = !p.self_prep;           // the planes of the mixing matrix are complete (self_prep: every CTA has announced)
       auto emit = [&](int type, int g, int t) {
+#ifdef MHLA_DIAG
         SpinGuard guard;
         while (pub - ld_acquire_cta_shared(q_started) >= run_ahead) {
           __nanosleep(32);
           if (guard.expired()) report_stall(3, pub, ld_acquire_cta_shared(q_started));
         }
+#else
+        uint32_t spins = 0;
+        while (pub - ld_acquire_cta_shared(q_started) >= run_ahead) {
+          __nanosleep(32);
+          if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: scheduler stalled (block %d)\n", blockIdx.x); __trap(); }
+        }
+#endif
         // (the slowest role is never more than a handful of items behind the producer: the ring, the two accumulators
         //  and the staging slots bound the distance well below kFifoDepth - run_ahead)
         *reinterpret_cast<volatile uint32_t*>(fifo + (pub & (kFifoDepth - 1))) = fifo_encode(type, g, t);
         st_release_cta_shared(q_published, ++pub);
       };
+#ifdef MHLA_DIAG
       SpinGuard idle;
+#else
+      uint32_t idle = 0;
+#endif
+      uint32_t wg_load[2] = {0, 0};   // epilogue work handed to each warpgroup so far (arbitrary units)
       long long cur1 = -1, cur2 = -1, cur3 = -1;   // claimed, not yet enqueued
-      // backwards readout (q_keep): the groups whose Q tiles the normaliser pulled in last come first, except that the
-      // final `tail` groups - whose block mixing is still in flight when the readout begins - come at the very end
-      const bool rev3 = dynamic && p.q_keep > 0 && p.G > 6;
-      const int tail = 3;
       while (true) {
         {  // claim what is missing; the atomics are independent and overlap
-          const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0;
+          const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0 && !(dedicated && (has2 || cur2 >= 0));
           unsigned long long a1 = 0, a2 = 0, a3 = 0;
           if (n1) a1 = atomicAdd(tickets + 0, 1ull);
           if (n2) a2 = atomicAdd(tickets + 8, 1ull);
           if (n3) a3 = atomicAdd(tickets + 16, 1ull);
           if (n1) {
             if ((long long)a1 < n1tot) cur1 = (long long)a1;
-            else { has1 = false; if (tl != nullptr) tl[2] = gtimer_ns(); }
+            else {
+              has1 = false;
+              if (tl != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[2] = t; }
+            }
           }
           if (n2) {
             if ((long long)a2 < n2tot) cur2 = (long long)a2;
-            else { has2 = false; if (tl != nullptr) tl[3] = gtimer_ns(); }
+            else {
+              has2 = false;
+              if (tl != nullptr) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[3] = t; }
+            }
           }
           if (n3) { if ((long long)a3 < n1tot) cur3 = (long long)a3; else has3 = false; }
         }
-        if (cur1 < 0 && cur2 < 0 && cur3 < 0) break;   // every kind is exhausted
+        if (cur1 < 0 && cur2 < 0 && cur3 < 0 && !(dedicated && has3)) break;   // every kind is exhausted
+        if (cur1 < 0 && cur2 < 0 && cur3 < 0) continue;                         // (dedicated CTA: now claim readout items)
         const int g2 = cur2 >= 0 ? (int)(cur2 / n2per) : -1;
         int g3 = cur3 >= 0 ? (int)(cur3 / p.M) : -1;
-        if (g3 >= 0 && rev3 && g3 < p.G - tail) g3 = p.G - tail - 1 - g3;
-        uint32_t c1 = 0, c2 = 0;
+        if (g3 >= 0 && rev3) g3 = p.G - 1 - g3;
+        // fused kernel with the readout last: walk the groups backwards (the Q tiles the normaliser pulled in last are
+        // still in L2), except that the final `tail` groups - whose block mixing is still in flight when the readout
+        // begins - come at the very end
+        if (g3 >= 0 && p.mode == 0 && p.policy == 1 && p.reverse3) {
+          const int tail = p.G > 6 ? 3 : 0;
+          if (g3 < p.G - tail) g3 = p.G - tail - 1 - g3;
+        }
         {  // both polls are in flight together: one L2 round trip per decision
-          const bool need1 = dep && g2 >= 0 && g2 != ready1_g, need2 = dep && g3 >= 0 && g3 != ready2_g;
+          const bool need1 = dep2 && g2 >= 0 && g2 != ready1_g, need2 = dep3 && g3 >= 0 && g3 != ready2_g;
+          uint32_t c1 = 0, c2 = 0;
           if (need1) c1 = ld_acquire_gpu(p.counters + (size_t)g2 * p.cnt_stride);
           if (need2) c2 = ld_acquire_gpu(p.counters + (size_t)(p.G + g3) * p.cnt_stride);
           if (need1 && c1 >= (uint32_t)p.M) ready1_g = g2;
           if (!w_ok && g2 >= 0) w_ok = ld_acquire_gpu(p.counters + (size_t)2 * p.G * p.cnt_stride + 64) >= gridDim.x;
           if (need2 && c2 >= (uint32_t)n2per) ready2_g = g3;
         }
-        const bool can2 = g2 >= 0 && (!dep || ready1_g == g2) && w_ok;
-        const bool can3 = g3 >= 0 && (!dep || ready2_g == g3);
-        if (can2) {
-          emit(2, g2, (int)(cur2 % n2per)); cur2 = -1; idle = SpinGuard();
-        } else if (cur1 >= 0) {
-          emit(1, (int)(cur1 / p.M), (int)(cur1 % p.M)); cur1 = -1; idle = SpinGuard();
-        } else if (can3) {
-          emit(3, g3, (int)(cur3 % p.M)); cur3 = -1; idle = SpinGuard();
+        const bool can2 = g2 >= 0 && (!dep2 || ready1_g == g2) && w_ok;
+        const bool can3 = g3 >= 0 && (!dep3 || ready2_g == g3);
+        const bool can1 = cur1 >= 0 && (p.mode != 0 || p.policy >= 1 || g3 < 0 || (int)(cur1 / p.M) < g3 + p.window);
+        // Items alternate between the two epilogue warpgroups (FIFO index parity) and a P1 epilogue (normaliser) costs
+        // about twice a P3 epilogue: when both kinds are available, give the heavier one to the less loaded warpgroup
+        // instead of letting a strict P1/P3 alternation pile every P1 item onto the same warpgroup.
+        int pick = 0;
+        if (can1 && p.policy == 2) pick = 1;          // policy 2: phase by phase (all summaries, then mixing, then readout)
+        else if (can2) pick = 2;
+        else if (can1 && p.policy == 1) pick = 1;
+        else if (can3 && can1) pick = (wg_load[pub & 1] <= wg_load[(pub & 1) ^ 1]) ? 1 : 3;
+        else if (can3) pick = 3;
+        else if (can1) pick = 1;
+        if (pick == 2) {
+          wg_load[pub & 1] += 8; emit(2, g2, (int)(cur2 % n2per)); cur2 = -1; idle = {};
+        } else if (pick == 3) {
+          wg_load[pub & 1] += 4; emit(3, g3, (int)(cur3 % p.M)); cur3 = -1; idle = {};
+        } else if (pick == 1) {
+          wg_load[pub & 1] += p.normalize ? 7 : 3; emit(1, (int)(cur1 / p.M), (int)(cur1 % p.M)); cur1 = -1; idle = {};
         } else {
           __nanosleep(100);
-          if (idle.expired())
-            report_stall(4, (uint32_t)(g2 & 0xFFFF) | ((uint32_t)(g3 & 0xFFFF) << 16), (c1 & 0xFFFF) | (c2 << 16));
+#ifdef MHLA_DIAG
+          if (idle.expired()) report_stall(4, (uint32_t)(g2 & 0xFFFF) | ((uint32_t)(g3 & 0xFFFF) << 16), 0);
+#else
+          if (++idle > (1u << 23)) { printf("mhla: dependency wait timed out (block %d)\n", blockIdx.x); __trap(); }
+#endif
         }
       }
       emit(0, 0, 0);
     }
   } else if (warp >= 4) {
-    // ============================================================ epilogue warpgroups (TMEM -> regs -> smem -> TMA store)
+    // ============================================================ epilogue warpgroups (TMEM -> regs -> smem -> global)
+    // Workspace results (S, n_loc, S~, den) leave through a swizzled staging slot and coalesced 16-byte global stores
+    // of the warpgroup itself - no TMA hand-off on the path that other CTAs are waiting for; completion is published
+    // through wg_done[wg] and turned into the group's arrival counter by the signal warp.  Only the readout tiles (O)
+    // go out by TMA (issued by thread 0 of the warpgroup, two slots in flight).
     const int q4 = warp & 3;                 // TMEM sub-partition (lanes 32*q4 .. 32*q4+31)
     const int wg = (warp - 4) >> 2;          // epilogue warpgroup: handles the items whose accumulator buffer is `wg`
     const int et = threadIdx.x - 128 - wg * kEpiThreads;   // 0..127 within the warpgroup
@@ -629,15 +774,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
     const int nslots = p.slots_per_wg;
     uint8_t* const my_staging = staging + wg * nslots * slot_bytes;
-    Ring r(nst);
+    Ring r(nst, wres ? p.kslabs : 0);
     uint32_t nitem = 0;
     uint32_t nchunk = 0;                     // staging chunks written so far (slot = nchunk & 1)
-    uint32_t ndone = 0;                      // workspace-producing items finished by this warpgroup
-    uint32_t npub = 0;                       // ... of which published through wg_done[wg] (thread 0's view)
+    uint32_t ndone = 0;                      // workspace-producing items finished (published through wg_done[wg])
+    int last_tma_slot = -1;                  // slot read by the most recent TMA store of this warpgroup (thread 0's view)
     uint32_t v[32];
     const bool prof_on = p.prof != nullptr && et == 0 && wg == 0;
-    long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_ld = 0, t_pack = 0, t_stage = 0, t_flush = 0;
-    const uint64_t ws_st_hint = p.ws_hint ? kEvictLast : kEvictNormal;
+    long long w_tfull = 0, w_sfree = 0, w_q = 0, t_p1 = 0, t_p2 = 0, t_p3 = 0, t_ld = 0, t_out = 0, t_pack = 0, t_stage = 0;
 
     // write one [rows][128 B] chunk row into the swizzle-128B staging tile
     auto stage_row = [&](uint8_t* buf, int row, const uint32_t* w32) {
@@ -648,28 +792,21 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         dst[c ^ (row & 7)] = make_uint4(w32[4 * c], w32[4 * c + 1], w32[4 * c + 2], w32[4 * c + 3]);
       if (prof_on) t_stage += clock64() - t0;
     };
-    // next staging slot; the TMA store that read it last (issued `nslots` chunks ago) must have finished reading
+    // next staging slot; a TMA store that is still reading it (issued two chunks ago) must have finished
     auto slot_acquire = [&]() -> uint8_t* {
       const int s_ = nslots == 1 ? 0 : (int)(nchunk & 1);
       const long long t0 = prof_on ? clock64() : 0;
-      if (et == 0) {
-        if (nslots == 1) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+      if (et == 0 && last_tma_slot >= 0) {
+        if (last_tma_slot == s_) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
       }
       named_bar_sync(bar_base + 1, kEpiThreads);
       if (prof_on) w_sfree += clock64() - t0;
       return my_staging + s_ * slot_bytes;
     };
-    // rows of the slot are complete: thread 0 sends it with TMA (one bulk group per chunk)
-    auto chunk_tma_begin = [&]() { fence_proxy_async_smem(); named_bar_sync(bar_base, kEpiThreads); };
-    auto chunk_tma_end = [&]() {
-      if (et == 0) tma_store_commit();
-      ++nchunk;
-    };
-    // rows of the slot are complete: copy [nrows][128 B] to global memory with plain 16-byte stores of the warpgroup,
-    // row r to gbase + r * row_stride (bytes).  Used for the small S tile of a P1 item: fire-and-forget stores keep the
-    // P1 epilogue short (a TMA store + completion wait costs it ~1200 cycles more, profiles/r02_notes.md).
+    // rows of the slot are complete: copy [nrows][128 B] to global memory, row r to gbase + r * row_stride (bytes)
     auto chunk_copy = [&](const uint8_t* buf, uint8_t* gbase, size_t row_stride, int nrows, int nvalid) {
       named_bar_sync(bar_base, kEpiThreads);
+      const long long t0 = prof_on ? clock64() : 0;
       // thread -> (row = k * 16 + et / 8, 16-byte piece et % 8): a warp instruction covers 4 rows x 128 contiguous bytes
       const int c = et & 7, r0_ = et >> 3;
       const uint8_t* sp = buf + r0_ * 128 + ((c ^ (r0_ & 7)) << 4);   // (k * 16 + r0_) & 7 == r0_ & 7
@@ -684,30 +821,20 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (k * 16 + r0_ < nvalid) __stcg(reinterpret_cast<uint4*>(gp + (size_t)k * 16 * row_stride), val[k]);
       };
       if (nrows == 64) run(std::integral_constant<int, 4>{}); else run(std::integral_constant<int, 8>{});
+      if (prof_on) t_out += clock64() - t0;
       ++nchunk;
     };
-    // every global store of a workspace item has been issued by all 128 threads: publish at once (plus any earlier item
-    // whose TMA stores are still unpublished - those have to land first)
-    auto publish_now = [&]() {
+    // rows of the slot are complete: thread 0 sends it with TMA
+    auto chunk_tma_begin = [&]() { fence_proxy_async_smem(); named_bar_sync(bar_base, kEpiThreads); };
+    auto chunk_tma_end = [&]() {
+      if (et == 0) { tma_store_commit(); last_tma_slot = nslots == 1 ? 0 : (int)(nchunk & 1); }
+      ++nchunk;
+    };
+    // every global store of this item has been issued by all 128 threads: publish
+    auto item_done = [&]() {
       named_bar_sync(bar_base + 3, kEpiThreads);
       ++ndone;
-      if (et == 0) {
-        if (npub + 1 != ndone) { tma_store_wait_all<0>(); fence_proxy_async_all(); }
-        npub = ndone;
-        st_release_cta_shared(&wg_done[wg], npub);
-      }
-    };
-    // Thread 0 of the warpgroup: every TMA store of the finished workspace items has landed -> publish them.  Called
-    // when the thread next looks at the FIFO (the stores were issued an item ago), never on the critical path.
-    auto flush = [&]() {
-      if (npub != ndone) {
-        const long long t0 = prof_on ? clock64() : 0;
-        tma_store_wait_all<0>();
-        fence_proxy_async_all();
-        npub = ndone;
-        st_release_cta_shared(&wg_done[wg], npub);
-        if (prof_on) t_flush += clock64() - t0;
-      }
+      if (et == 0) st_release_cta_shared(&wg_done[wg], ndone);
     };
     // load 64 fp32 accumulator columns, scale, round to the 16-bit I/O type: 32 packed words = one 128-byte row
     auto load_pack64 = [&](uint32_t taddr, float scale, uint32_t* pk) {
@@ -820,23 +947,11 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       named_bar_sync(9, 256);
       if (t256 == 0) red_release_gpu_add(p.counters + (size_t)2 * p.G * p.cnt_stride + 64, 1u);
     }
-    while (true) {
-      // whole-warp poll of the item FIFO: lane 0 spins, the warp then reads the entry together.  Thread 0 of the
-      // warpgroup uses an empty FIFO to publish finished items (their TMA stores have landed by now).
-      if (lane == 0) {
-        SpinGuard guard;
-        while (!sched.ready()) {
-          if (et == 0) flush();
-          __nanosleep(32);
-          if (guard.expired()) report_stall(2, 2 + wg, sched.idx);
-        }
-      }
-      __syncwarp();
-      if (!sched.take(it)) break;
+    while (sched.next_warp(it, lane)) {
       const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
       const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
       if ((int)ab != wg) {   // the other warpgroup's item: only keep the ring bookkeeping in step
-        r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? 2 * p.kslabs : p3_stages<D>(p)));
+        r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? (wres ? 1 : 2) * p.kslabs : p3_stages<D>(p)));
         ++nitem;
         continue;
       }
@@ -890,7 +1005,6 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               r.advance();
             }
           }
-          // (the n_loc stores of all 128 threads precede the barrier above, hence thread 0's later publication)
         }
         for (int c = 0; c < D / 64; ++c) {
           uint32_t pk[32];
@@ -902,30 +1016,23 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        publish_now();
+        item_done();
       } else if (it.type == 2) {
         const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+        const int nvalid = p.M - ti * 128;       // rows of this tile inside the matrix (TMA used to clip them)
+        const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
-        if (et == 0) { trace_ev(p, 2, nitem, 1); flush(); }
+        if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         const float wsc = p.self_prep ? *wscale_s : __ldg(p.wscale);   // undo the power-of-two normalisation (exact)
-        // (rows beyond the matrix - the last row tile of M = 150 - are clipped by the TMA store / the nvalid guard)
-        const int nvalid = p.M - ti * 128;
-        const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
         if (tc < p.n2_scols) {
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
             load_pack64(acc + c * 64, wsc, pk);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
-            if (p.p2_tma) {
-              chunk_tma_begin();
-              if (et == 0) tma_store_3d_hint(&p.tmStst, buf, tc * 256 + c * 64, ti * 128, it.g, ws_st_hint);
-              chunk_tma_end();
-            } else {
-              chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
-                         (size_t)D * D * 2, 128, nvalid);
-            }
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
+                       (size_t)D * D * 2, 128, nvalid);
           }
         } else {
           for (int q = 0; q < 8; ++q) {
@@ -937,22 +1044,15 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * wsc);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, v);
-            if (p.p2_tma) {
-              chunk_tma_begin();
-              if (et == 0) tma_store_3d_hint(&p.tmDen, buf, col0, ti * 128, it.g, ws_st_hint);
-              chunk_tma_end();
-            } else {
-              chunk_copy(buf, reinterpret_cast<uint8_t*>(const_cast<float*>(p.den) + row0 * (size_t)(2 * p.wpad) + col0),
-                         (size_t)2 * p.wpad * 4, 128, nvalid);
-            }
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(const_cast<float*>(p.den) + row0 * (size_t)(2 * p.wpad) + col0),
+                       (size_t)2 * p.wpad * 4, 128, nvalid);
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
-        r.advance(2 * p.kslabs);
-        if (p.p2_tma) ++ndone;   // lazy: published by flush() once the TMA stores have landed
-        else publish_now();
+        r.advance((wres ? 1 : 2) * p.kslabs);
+        item_done();
       } else {
         const int i = it.t;                               // block row within the scheduled (packed) group
         const int gr = it.g * p.pack + it.t / p.M0;       // real (b,h) group and block inside it: tensor coordinates
@@ -970,7 +1070,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           }
         }
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
-        if (et == 0) { trace_ev(p, 2, nitem, 1); flush(); }
+        if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
@@ -1000,7 +1100,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_tma_begin();
-            // the output is never read again: mark its lines evict-first so that they leave L2 before anything useful
+            // the output is never read again: mark its lines evict-first so that they leave L2 before the Q tiles the
+            // readout of later groups still needs
             if (et == 0) tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, ib, h, b, p.o_hint ? kEvictFirst : kEvictNormal);
             chunk_tma_end();
           }
@@ -1017,35 +1118,42 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       }
       ++nitem;
     }
-    if (et == 0) { flush(); tma_store_wait_all<0>(); }
+    if (et == 0) tma_store_wait_all<0>();
     if (prof_on) {
       unsigned long long* pr = p.prof + (size_t)blockIdx.x * 16;
-      pr[5] = (unsigned long long)w_tfull; pr[6] = (unsigned long long)w_sfree; pr[7] = (unsigned long long)t_pack;
+      pr[5] = (unsigned long long)w_tfull; pr[6] = (unsigned long long)w_sfree; pr[7] = (unsigned long long)w_q;
       pr[8] = (unsigned long long)t_p1; pr[9] = (unsigned long long)t_p2; pr[10] = (unsigned long long)t_p3;
       pr[11] = nitem;
-      pr[12] = (unsigned long long)t_ld; pr[13] = (unsigned long long)t_flush;
-      pr[15] = (unsigned long long)t_stage;
-      (void)w_q;
+      pr[12] = (unsigned long long)t_ld; pr[13] = (unsigned long long)t_out;
+      pr[7] = (unsigned long long)t_pack; pr[15] = (unsigned long long)t_stage;
     }
   } else if (warp == 3) {
     // ============================================================ signal warp (one lane)
-    // Turns "warpgroup published item n" (wg_done, shared memory) into the group's arrival counter in global memory.
-    // The release (gpu scope) orders the item's results before the increment: the TMA stores have completed
-    // (cp.async.bulk.wait_group by the issuing thread) and the n_loc stores of the warpgroup's 128 threads happen before
-    // its named barrier, thread 0's st.release.cta and this lane's ld.acquire.cta.
+    // Turns "warpgroup finished item n" (wg_done, shared memory) into the group's arrival counter in global memory.
+    // The release (gpu scope) orders every global store of the warpgroup's 128 threads before the increment: they
+    // happen before the warpgroup's named barrier, thread 0's st.release.cta and this lane's ld.acquire.cta.  The
+    // ~1 us the release takes under load is spent here, not in the epilogue.
     if (dynamic && elect_one()) {
       uint32_t seen[2] = {0, 0};
       uint32_t n = 0;
-      while (sched.next(it, 1 + 3)) {
+      while (sched.next(it)) {
         const int wgi = (int)(n & 1);
         trace_ev(p, 3, n, 0);
         if (it.type != 3) {
           ++seen[wgi];
+#ifdef MHLA_DIAG
           SpinGuard guard;
           while (ld_acquire_cta_shared(&wg_done[wgi]) < seen[wgi]) {
             __nanosleep(32);
             if (guard.expired()) report_stall(5, (uint32_t)wgi, seen[wgi]);
           }
+#else
+          uint32_t spins = 0;
+          while (ld_acquire_cta_shared(&wg_done[wgi]) < seen[wgi]) {
+            __nanosleep(32);
+            if (++spins > MHLA_SPIN_LIMIT) { printf("mhla: signal wait timed out (block %d)\n", blockIdx.x); __trap(); }
+          }
+#endif
           trace_ev(p, 3, n, 1);
           red_release_gpu_add(p.counters + (size_t)((it.type == 1 ? 0 : p.G) + it.g) * p.cnt_stride, 1u);
         }
@@ -1058,7 +1166,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   // ---------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
-  if (tl != nullptr && threadIdx.x == 0) tl[1] = gtimer_ns();
+  if (tl != nullptr && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); tl[1] = t; }
   if (warp == 2) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
   if (p.self_prep) {
     // The last CTA to get here re-zeroes the control block (counters, tickets, flags) for the next call: every other

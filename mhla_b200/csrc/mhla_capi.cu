@@ -80,7 +80,7 @@ constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (sepa
 
 // Tuning / debugging knobs of the blockmix kernel, read from the environment ONCE (first call).
 struct Knobs {
-  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, ws_hint = 1, q_keep = 0, trace_cta = 0, slots = 2, p2_tma = 1;
+  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, q_hint = 1, trace_cta = 0, slots = 2;
   bool no_pack = false, no_self_prep = false;
 };
 const Knobs& knobs() {
@@ -93,9 +93,7 @@ const Knobs& knobs() {
     if (k.run_ahead > 16) k.run_ahead = 16;
     k.mix_hi_only = geti("MHLA_MIX_HI_ONLY", 0);
     k.o_hint = geti("MHLA_OHINT", 1);
-    k.ws_hint = geti("MHLA_WSHINT", 1);
-    k.q_keep = geti("MHLA_QKEEP", 0);
-    k.p2_tma = geti("MHLA_P2TMA", 1);
+    k.q_hint = geti("MHLA_QHINT", 1);
     k.trace_cta = geti("MHLA_TRACE_CTA", 0);
     k.slots = geti("MHLA_SLOTS", 2) == 1 ? 1 : 2;
     k.no_pack = std::getenv("MHLA_NO_PACK") != nullptr;
@@ -377,6 +375,14 @@ size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc) {
   return pl.total;
 }
 
+/* 1 when mhla_fwd_blockmix(desc) will touch the workspace, 0 when the shape takes the short-sequence kernel (whole unit
+ * on chip, csrc/smalln_kernel.cuh) and workspace may be NULL. */
+int mhla_blockmix_needs_workspace(const mhla_blockmix_desc* desc) {
+  BlockmixPlan pl;
+  if (plan_blockmix(desc, &pl) != MHLA_OK) return 1;
+  return smalln_eligible(desc) ? 0 : 1;
+}
+
 int mhla_blockmix_workspace_layout(const mhla_blockmix_desc* desc, size_t out[8]) {
   BlockmixPlan pl;
   int rc = plan_blockmix(desc, &pl);
@@ -429,9 +435,8 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.trace_cta = kn.trace_cta;
   P.mix_hi_only = kn.mix_hi_only;
   P.o_hint = kn.o_hint;
-  P.ws_hint = kn.ws_hint;
-  P.q_keep = kn.q_keep;
-  P.p2_tma = kn.p2_tma;
+  P.q_hint = kn.q_hint;
+  P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = 0;   // (round-1 tuning options, fixed at their best values)
   auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -530,7 +535,7 @@ int mhla_blockmix_workspace_init(const mhla_blockmix_desc* d, void* stream_) {
   return MHLA_OK;
 }
 
-namespace { __global__ void stall_selftest_kernel() { mhla::report_stall(99, 1, 2); } }
+namespace { __global__ void stall_selftest_kernel() { mhla::report_stall_diag(99, 1, 2); } }
 /* Debug hook: launches one thread that reports a stall (code 99) and traps - checks the diagnostics path end to end. */
 int mhla_debug_trigger_stall(void* stream_) {
   stall_selftest_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>();

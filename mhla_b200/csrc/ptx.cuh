@@ -9,9 +9,18 @@
 
 namespace mhla {
 
-// A wait that never completes would hang the GPU box: every spin is bounded in TIME (globaltimer) and, when the bound
-// expires, records who was waiting for what in a host-mapped diagnostics buffer (if the host installed one with
-// mhla_debug_set_diag_buffer), lingers long enough for the other stalled roles to record themselves too, and traps.
+// A wait that never completes would hang the GPU box, so every spin is bounded and traps when the bound expires.
+// Two builds:
+//  * default (product): iteration-count bounds and a printf + trap in the cold branch - the lean loops of round 1.  The
+//    single-lane roles share their warp schedulers with the epilogue warps, so every extra instruction in a polling
+//    loop is an issue slot taken from them: moving these loops to a time-based bound with an out-of-line reporter cost
+//    the headline kernel 3-9 % (profiles/r02_notes.md), hence the two builds.
+//  * -DMHLA_DIAG (libmhla_b200_diag.so, tools/stress.py): bounds in TIME (globaltimer) and, when one expires, a record of
+//    who was waiting for what in a host-mapped diagnostics buffer (mhla_debug_set_diag_buffer) before the trap - the
+//    build the round-2 stall investigation was done with (profiles/r02_stall_root_cause.md).
+#ifndef MHLA_SPIN_LIMIT
+#define MHLA_SPIN_LIMIT (1u << 26)
+#endif
 #ifndef MHLA_STALL_NS
 #define MHLA_STALL_NS 8000000000ull   /* 8 s: far beyond any legitimate wait (a whole launch takes < 1 ms) */
 #endif
@@ -25,8 +34,8 @@ __device__ __forceinline__ unsigned long long gtimer_ns() {
 }
 
 // codes: 1 mbarrier (a = shared address, b = parity)   2 item stream (a = role, b = index)   3 scheduler throttle
-//        4 scheduler idle (a = claimed kinds, b = counter value)   5 signal warp (a = warpgroup, b = seen)   6 counter spin
-__device__ __noinline__ void report_stall(uint32_t code, uint32_t a, uint32_t b) {
+//        4 scheduler idle (a = claimed groups)   5 signal warp (a = warpgroup, b = seen)   6 counter spin   99 self-test
+__device__ __noinline__ void report_stall_diag(uint32_t code, uint32_t a, uint32_t b) {
   unsigned long long* d = g_mhla_diag;
   if (d != nullptr) {
     // one record of 4 words per (block, warp): [code | thread << 32, a | b << 32, clock64, globaltimer]
@@ -43,6 +52,8 @@ __device__ __noinline__ void report_stall(uint32_t code, uint32_t a, uint32_t b)
   __trap();
 }
 
+#ifdef MHLA_DIAG
+__device__ __forceinline__ void report_stall(uint32_t code, uint32_t a, uint32_t b) { report_stall_diag(code, a, b); }
 struct SpinGuard {
   uint32_t n = 0;
   unsigned long long t0 = 0;
@@ -54,6 +65,16 @@ struct SpinGuard {
     return t - t0 > MHLA_STALL_NS;
   }
 };
+#else
+__device__ __forceinline__ void report_stall(uint32_t code, uint32_t, uint32_t) {
+  printf("mhla: wait %u timed out (block %d)\n", code, blockIdx.x);
+  __trap();
+}
+struct SpinGuard {
+  uint32_t n = 0;
+  __device__ __forceinline__ bool expired() { return ++n > MHLA_SPIN_LIMIT; }
+};
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -95,10 +116,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef MHLA_DIAG
   SpinGuard guard;
   while (!mbar_try_wait(bar, parity)) {
     if (guard.expired()) report_stall(1, smem_u32(bar), parity);
   }
+#else
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > MHLA_SPIN_LIMIT) {
+      printf("mhla: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  }
+#endif
 }
 
 // ---------------------------------------------------------------- proxies / fences

@@ -17,7 +17,45 @@ import torch.nn as nn
 import torch.nn.functional as F
 from einops import rearrange, repeat
 
-from ..ops import naive_chunk_simple_mhla_fixed, naive_recurrent_mhla
+from ..decode import MHLAState, causal_with_state, get_unpad_data, pad_input
+from ..ops import mhla_causal, naive_chunk_simple_mhla_fixed, naive_recurrent_mhla  # noqa: F401
+
+
+class Cache:
+    """The slice of ``fla.models.utils.Cache`` the layer uses (layers/mhla.py:247-252,301-348): per-layer dicts with
+    ``recurrent_state`` / ``conv_state``, ``update(...)`` and ``get_seq_length``.  ``recurrent_state`` holds an
+    ``MHLAState`` (completed chunk summaries + the open chunk's k, v rows) - a state that actually continues the
+    sequence, unlike the reference's all-zero one."""
+
+    def __init__(self, seen_tokens: int = 0):
+        self.states = []
+        self._seen_tokens = seen_tokens
+
+    def __getitem__(self, layer_idx):
+        return self.states[layer_idx]
+
+    def __len__(self):
+        return len(self.states)
+
+    def update(self, recurrent_state=None, attn_state=None, conv_state=None, ffn_state=None, layer_idx=0, offset=1,
+               cache_kwargs=None):
+        if layer_idx == 0:
+            self._seen_tokens += offset
+        if len(self.states) <= layer_idx:
+            self.states.append(dict(recurrent_state=recurrent_state, attn_state=attn_state, conv_state=conv_state,
+                                    ffn_state=ffn_state))
+        else:
+            st = self.states[layer_idx]
+            if recurrent_state is not None:
+                st["recurrent_state"] = recurrent_state
+            if conv_state is not None:
+                st["conv_state"] = conv_state
+        return self.states[layer_idx]
+
+    def get_seq_length(self, layer_idx=0):
+        if len(self.states) <= layer_idx:
+            return 0
+        return self._seen_tokens
 
 
 class RotaryEmbedding(nn.Module):
@@ -30,12 +68,20 @@ class RotaryEmbedding(nn.Module):
         self.register_buffer("inv_freq", inv, persistent=False)
 
     def forward(self, q, k, seqlen_offset=0, max_seqlen=None, cu_seqlens=None):
-        if cu_seqlens is not None:
-            raise NotImplementedError("variable-length (cu_seqlens) rotary is a next-row item")
         T = q.shape[1]
         off = int(seqlen_offset) if not torch.is_tensor(seqlen_offset) else seqlen_offset
         t = torch.arange(T, device=q.device, dtype=torch.float32)
-        if torch.is_tensor(off):
+        if cu_seqlens is not None:
+            # packed batch [1, total, ...]: positions restart at every sequence start (fla/modules/rotary.py, varlen path)
+            cu = cu_seqlens.to(device=q.device, dtype=torch.long)
+            seq_id = torch.bucketize(torch.arange(T, device=q.device), cu[1:], right=True)
+            t = (t - cu[seq_id].float())
+            if torch.is_tensor(off):
+                t = t + off.to(t)[seq_id]
+            else:
+                t = t + off
+            t = t[None, :]
+        elif torch.is_tensor(off):
             t = t[None, :] + off.to(t)[:, None]
         else:
             t = (t + off)[None, :]
@@ -77,17 +123,37 @@ class ShortConvolution(nn.Conv1d):
     """Depthwise causal conv over time followed by SiLU (fla/modules/convolution.py); weight [hidden, 1, k]."""
 
     def __init__(self, hidden_size, kernel_size, bias=False, activation="silu"):
-        super().__init__(hidden_size, hidden_size, kernel_size, groups=hidden_size, bias=bias, padding=kernel_size - 1)
+        super().__init__(hidden_size, hidden_size, kernel_size, groups=hidden_size, bias=bias, padding=0)
         self.hidden_size, self.activation = hidden_size, activation
 
     def forward(self, x, cache=None, output_final_state=False, cu_seqlens=None):
-        if cache is not None or cu_seqlens is not None:
-            raise NotImplementedError("short-conv state caching / varlen is a next-row item")
-        T = x.shape[1]
-        y = super().forward(x.transpose(1, 2))[..., :T].transpose(1, 2)
+        """x [B, T, C] -> (y, final_state): causal depthwise conv.  ``cache`` [B, C, k-1] holds the previous inputs
+        (decode); ``cu_seqlens`` (packed batch, B = 1) keeps the window from reaching across sequence starts."""
+        B, T, Cc = x.shape
+        kw_ = self.kernel_size[0]
+        xt = x.transpose(1, 2)                                                      # [B, C, T]
+        left = cache.to(xt.dtype) if cache is not None else xt.new_zeros(B, Cc, kw_ - 1)
+        xp = torch.cat([left, xt], dim=-1)                                          # [B, C, T + k - 1]
+        if cu_seqlens is not None:
+            # zero the taps that would read the previous sequence: tap d of token t is valid iff t - d >= its sequence start
+            cu = cu_seqlens.to(device=x.device, dtype=torch.long)
+            pos = torch.arange(T, device=x.device)
+            start = cu[torch.bucketize(pos, cu[1:], right=True)]
+            w = self.weight[:, 0, :]                                                # [C, k], tap j multiplies x[t - (k-1-j)]
+            y = xt.new_zeros(B, Cc, T)
+            for j in range(kw_):
+                d = kw_ - 1 - j
+                ok = (pos - d >= start).to(xt.dtype)
+                y = y + xp[..., j:j + T] * w[:, j].view(1, -1, 1) * ok.view(1, 1, -1)
+            if self.bias is not None:
+                y = y + self.bias.view(1, -1, 1)
+        else:
+            y = F.conv1d(xp, self.weight, self.bias, groups=Cc)
+        y = y.transpose(1, 2)
         if self.activation in ("silu", "swish"):
             y = F.silu(y)
-        return y, None
+        final = xp[..., -(kw_ - 1):].contiguous() if output_final_state else None
+        return y, final
 
 
 _ACT = {"swish": F.silu, "silu": F.silu, "sigmoid": torch.sigmoid, "relu": F.relu, "gelu": F.gelu}
@@ -99,9 +165,15 @@ class MHLA(nn.Module):
                  use_short_conv: bool = False, conv_size: int = 4, conv_bias: bool = False,
                  use_output_gate: bool = True, gate_fn: str = "swish", elementwise_affine: Optional[bool] = True,
                  norm_eps: float = 1e-5, gate_logit_normalizer: int = 16, gate_low_rank_dim: int = 16,
-                 clamp_min: Optional[float] = None, fuse_norm: bool = True, layer_idx: int = None):
+                 clamp_min: Optional[float] = None, fuse_norm: bool = True, layer_idx: int = None,
+                 max_chunks: int = 32, varlen: str = "reference"):
+        """``max_chunks`` (extension): side of the mixing matrix, 32 in the reference (layers/mhla.py:196) - sequences
+        longer than 32 * 64 tokens need more.  ``varlen`` (extension): "reference" evaluates a padded batch as the
+        reference does - un-padded and packed into ONE sequence (layers/mhla.py:254-256; chunks run across sequence
+        borders); "per_sequence" evaluates every sequence on its own."""
         super().__init__()
         self.mode = mode
+        self.varlen = varlen
         self.hidden_size = hidden_size
         self.expand_k, self.expand_v = expand_k, expand_v
         self.num_heads = num_heads
@@ -148,7 +220,7 @@ class MHLA(nn.Module):
             self.k_conv1d = ShortConvolution(self.key_dim_per_group, conv_size, bias=conv_bias, activation="silu")
             self.v_conv1d = ShortConvolution(self.value_dim_per_group, conv_size, bias=conv_bias, activation="silu")
 
-        L = 32                                                         # layers/mhla.py:196-200
+        L = int(max_chunks)                                            # 32: layers/mhla.py:196-200
         lower_tri = torch.tril(torch.ones(L, L, dtype=torch.float32))
         lower_tri = lower_tri / (torch.arange(L, dtype=torch.float32).unsqueeze(1) + 1.0)
         self.mixing_matrix = nn.Parameter(lower_tri.view(L, L, 1, 1, 1, 1))
@@ -172,17 +244,29 @@ class MHLA(nn.Module):
         self.mixing_matrix.data = torch.clamp(self.mixing_matrix.data, 1e-5, 1).tril()
         if attention_mask is not None:
             assert len(attention_mask.shape) == 2, "Expected attention_mask as a 0-1 matrix with shape [batch_size, seq_len]"
-            if not bool(attention_mask.all()):
-                raise NotImplementedError("padding masks (varlen unpad) are a next-row item (SURVEY.md 8f rank 4)")
-        if kwargs.get("cu_seqlens") is not None:
-            raise NotImplementedError("cu_seqlens packing is a next-row item (SURVEY.md 8f rank 4)")
         batch_size, q_len, _ = hidden_states.shape
-        mode = "fused_recurrent" if q_len <= 64 else self.mode
+        layer = self.layer_idx if self.layer_idx is not None else 0
+        last_state = None
+        if past_key_values is not None and len(past_key_values) > layer:
+            last_state = past_key_values[layer]
 
+        cu_seqlens = kwargs.get("cu_seqlens", None)
+        indices = None
+        if attention_mask is not None and not bool(attention_mask[:, -q_len:].all()):
+            if last_state is not None:
+                raise NotImplementedError("decoding with a padded batch is not supported (left-pad the prompts instead)")
+            indices, cu_seqlens, _ = get_unpad_data(attention_mask[:, -q_len:])            # layers/mhla.py:254-256
+            hidden_states = hidden_states.reshape(batch_size * q_len, -1)[indices].unsqueeze(0)
+
+        conv_state = None
         if self.use_short_conv:
-            q, _ = self.q_conv1d(self.q_proj(hidden_states))
-            k, _ = self.k_conv1d(self.k_proj(hidden_states))
-            v, _ = self.v_conv1d(self.v_proj(hidden_states))
+            cq = ck = cv = None
+            if last_state is not None and last_state.get("conv_state") is not None:
+                cq, ck, cv = last_state["conv_state"]
+            q, cq = self.q_conv1d(self.q_proj(hidden_states), cache=cq, output_final_state=use_cache, cu_seqlens=cu_seqlens)
+            k, ck = self.k_conv1d(self.k_proj(hidden_states), cache=ck, output_final_state=use_cache, cu_seqlens=cu_seqlens)
+            v, cv = self.v_conv1d(self.v_proj(hidden_states), cache=cv, output_final_state=use_cache, cu_seqlens=cu_seqlens)
+            conv_state = (cq, ck, cv)
         else:
             q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
         q = rearrange(q, "... (h d) -> ... h d", d=self.head_k_dim)
@@ -196,22 +280,29 @@ class MHLA(nn.Module):
 
         seqlen_offset = 0
         if past_key_values is not None:
-            seqlen_offset = past_key_values.get_seq_length(self.layer_idx)
-        q, k = self.rotary(q, k, seqlen_offset=seqlen_offset)
+            seqlen_offset = past_key_values.get_seq_length(layer)
+        q, k = self.rotary(q, k, seqlen_offset=seqlen_offset, cu_seqlens=cu_seqlens)
 
-        if mode == "fused_recurrent":
-            o, recurrent_state = naive_recurrent_mhla(q=q, k=k, v=v, mixing_matrix=self.mixing_matrix,
-                                                      initial_state=None, output_final_state=use_cache)
-        elif mode == "chunk":
-            o = naive_chunk_simple_mhla_fixed(q=q, k=k, v=v, mixing_matrix=self.mixing_matrix,
-                                              output_final_state=use_cache)
-            recurrent_state = None
+        prev = last_state["recurrent_state"] if last_state is not None else None
+        if self.mode not in ("chunk", "fused_recurrent"):
+            raise NotImplementedError(f"Not supported mode `{self.mode}`.")
+        recurrent_state = None
+        if isinstance(prev, MHLAState) or use_cache:
+            # stateful evaluation: the prompt runs through the kernel, continuations are evaluated from the chunk
+            # summaries kept in the cache (mhla_b200/decode.py)
+            o, recurrent_state = causal_with_state(q, k, v, self.mixing_matrix, prev, prefill_op=mhla_causal)
+        elif indices is not None and self.varlen == "per_sequence":
+            cu = cu_seqlens.tolist()
+            o = torch.cat([mhla_causal(q[:, a:b], k[:, a:b], v[:, a:b], self.mixing_matrix) for a, b in zip(cu[:-1], cu[1:])], dim=1)
+        elif q.shape[1] <= 64:        # layers/mhla.py:247: 'fused_recurrent' for short inputs; equals the chunk form there
+            o, _ = naive_recurrent_mhla(q=q, k=k, v=v, mixing_matrix=self.mixing_matrix, initial_state=None,
+                                        output_final_state=False)
         else:
-            raise NotImplementedError(f"Not supported mode `{mode}`.")
+            o = naive_chunk_simple_mhla_fixed(q=q, k=k, v=v, mixing_matrix=self.mixing_matrix, output_final_state=use_cache)
 
         if past_key_values is not None:
-            past_key_values.update(recurrent_state=recurrent_state, conv_state=None, layer_idx=self.layer_idx,
-                                   offset=q_len)
+            past_key_values.update(recurrent_state=recurrent_state, conv_state=conv_state if self.use_short_conv else None,
+                                   layer_idx=layer, offset=q_len)
         if self.use_output_gate:
             g = self.g_proj(hidden_states)
             if self.fuse_norm_and_gate:
@@ -222,4 +313,6 @@ class MHLA(nn.Module):
         else:
             o = rearrange(self.g_norm(o), "... h d -> ... (h d)")
         o = self.o_proj(o)
+        if indices is not None:
+            o = pad_input(o.squeeze(0), indices, batch_size, q_len)                         # layers/mhla.py:362-363
         return o, None, past_key_values

@@ -71,14 +71,19 @@ class _Local(__import__("threading").local):
 _TLS = _Local()
 
 
-def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int, sig: tuple) -> torch.Tensor:
+def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int, sig: tuple, off_cnt: int) -> torch.Tensor:
     # keyed by the full call signature: two shapes of equal total size lay the control block out differently
     key = (device.index, stream_handle, nbytes) + tuple(sig)
     ws = _WS_CACHE.get(key)
     if ws is None:
         if len(_WS_CACHE) >= _WS_CACHE_MAX:
             _WS_CACHE.pop(next(iter(_WS_CACHE)))
-        ws = torch.zeros(nbytes + 1024, dtype=torch.uint8, device=device)
+        # only the control block (dependency counters, tickets, flags) has to start out zero - the kernel keeps it
+        # that way; zeroing just that keeps a CUDA-graph capture of the first call from recording a memset of the
+        # whole (tens of MB) workspace that every replay would repeat
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+        base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+        ws[base + off_cnt:].zero_()
         _WS_CACHE[key] = ws
     return ws
 
@@ -178,7 +183,7 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         flags |= _capi.FLAG_WS_PERSISTENT | (_capi.FLAG_FUSED if force_fused else 0)
     L = _capi.lib()
     # the descriptor (shape, flags, workspace size) is cached per call signature; only pointers and strides change
-    sig = (B, H, M, w, D, cdtype, flags, float(eps))
+    sig = (B, H, M, w, D, cdtype, flags, float(eps), qr5 is not None, out_rms_weight is not None)
     cache = _TLS.desc
     ent = cache.get(sig)
     if ent is None:
@@ -191,10 +196,16 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         if nbytes == 0:
             raise _capi.MhlaError(
                 f"unsupported blockmix shape B={B} H={H} M={M} w={w} D={D} (need D in {{64,128}}, w<=256)")
+        # short sequences (no rope, no fused output norm) run without a workspace (csrc/smalln_kernel.cuh)
+        d.q_rope.ptr, d.k_rope.ptr = (1 if qr5 is not None else None), (1 if kr5 is not None else None)
+        d.out_rms_weight = 1 if out_rms_weight is not None else None
+        needs_ws = bool(L.mhla_blockmix_needs_workspace(C.byref(d))) if hasattr(L, "mhla_blockmix_needs_workspace") else True
+        lay = (C.c_size_t * 8)()
+        _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
         if len(cache) > 64:
             cache.clear()
-        ent = cache[sig] = (d, nbytes)
-    d, nbytes = ent
+        ent = cache[sig] = (d, nbytes, needs_ws, int(lay[4]))
+    d, nbytes, needs_ws, off_cnt = ent
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)
     d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
@@ -205,11 +216,14 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
             raise ValueError(f"out_rms_weight must have {D} elements")
     d.out_rms_weight, d.out_rms_eps = (rms_w.data_ptr() if rms_w is not None else None), float(out_rms_eps)
     stream = torch.cuda.current_stream(q.device)
-    if single:
-        ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig)
+    if not needs_ws:
+        d.workspace, d.workspace_bytes = None, 0
     else:
-        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
-    d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
+        if single:
+            ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig, off_cnt)
+        else:
+            ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+        d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
     if torch.cuda.current_device() == q.device.index:
         _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
     else:

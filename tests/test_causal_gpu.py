@@ -116,3 +116,81 @@ def test_nlp_layer_forward_runs_and_matches_oracle_composition():
         gate = m.g_proj(x).view(2, 256, 2, 256)
         ref = m.o_proj(m.g_norm_swish_gate(oc.cuda().bfloat16(), gate).reshape(2, 256, 512))
     assert oracle.err_ratio(ref.float().cpu(), o.float().cpu()) < 2e-2
+
+
+def test_nlp_layer_prefill_then_decode_equals_full_forward():
+    """use_cache: the prompt runs through the kernel, the cache keeps the chunk summaries + the open chunk, and the decode
+    steps continue the sequence exactly (the reference's cache cannot: its recurrent state is all zeros)."""
+    from mhla_b200.modules import MHLA
+    from mhla_b200.modules.nlp import Cache
+    torch.manual_seed(0)
+    for conv in (False, True):
+        m = MHLA(mode="chunk", hidden_size=256, expand_k=0.5, expand_v=1.0, num_heads=2, feature_map="relu",
+                 use_short_conv=conv, layer_idx=0).cuda().bfloat16().eval()
+        x = torch.randn(2, 150, 256, device="cuda", dtype=torch.bfloat16)
+        with torch.no_grad():
+            full, _, _ = m(x)
+            cache = Cache()
+            o0, _, cache = m(x[:, :140], past_key_values=cache, use_cache=True)
+            outs = [o0]
+            for t in range(140, 150):
+                ot, _, cache = m(x[:, t:t + 1], past_key_values=cache, use_cache=True)
+                outs.append(ot)
+        assert cache.get_seq_length(0) == 150
+        assert oracle.err_ratio(full.float().cpu(), torch.cat(outs, dim=1).float().cpu()) < 2e-2
+
+
+def test_nlp_layer_padded_batch_modes():
+    """attention_mask with right padding: 'reference' packs the real tokens into ONE sequence like layers/mhla.py:254-256,
+    'per_sequence' (extension) evaluates every sequence on its own; padded positions come back as zeros."""
+    from mhla_b200.modules import MHLA
+    torch.manual_seed(1)
+    lens = [200, 131]
+    x = torch.randn(2, 200, 256, device="cuda", dtype=torch.bfloat16)
+    mask = torch.zeros(2, 200, dtype=torch.long, device="cuda")
+    for b, n in enumerate(lens):
+        mask[b, :n] = 1
+    for mode in ("reference", "per_sequence"):
+        m = MHLA(mode="chunk", hidden_size=256, num_heads=2, feature_map="relu", varlen=mode).cuda().bfloat16().eval()
+        with torch.no_grad():
+            o, _, _ = m(x, attention_mask=mask)
+            assert o.shape == x.shape and float(o[1, 131:].abs().max()) == 0.0
+            if mode == "per_sequence":
+                for b, n in enumerate(lens):
+                    ob, _, _ = m(x[b:b + 1, :n])
+                    assert oracle.err_ratio(ob.float().cpu(), o[b:b + 1, :n].float().cpu()) < 1e-2
+            else:
+                packed = torch.cat([x[0, :200], x[1, :131]], dim=0).unsqueeze(0)
+                cu = torch.tensor([0, 200, 331], dtype=torch.int32, device="cuda")
+                op, _, _ = m(packed, cu_seqlens=cu)
+                assert oracle.err_ratio(op[0, 200:].float().cpu(), o[1, :131].float().cpu()) < 1e-2
+
+
+def test_nlp_layer_longer_than_32_chunks():
+    from mhla_b200.modules import MHLA
+    m = MHLA(mode="chunk", hidden_size=128, num_heads=1, feature_map="relu", max_chunks=64).cuda().bfloat16().eval()
+    assert tuple(m.mixing_matrix.shape) == (64, 64, 1, 1, 1, 1)
+    with torch.no_grad():
+        o, _, _ = m(torch.randn(1, 4096, 128, device="cuda", dtype=torch.bfloat16))
+    assert torch.isfinite(o.float()).all()
+    m32 = MHLA(mode="chunk", hidden_size=128, num_heads=1, feature_map="relu").cuda().bfloat16().eval()
+    with pytest.raises(IndexError):
+        m32(torch.randn(1, 4096, 128, device="cuda", dtype=torch.bfloat16))
+
+
+def test_causal_backward_through_the_kernel():
+    """Training: CUDA forward + analytic backward (mhla_b200/autograd.py) against autograd of the oracle."""
+    import mhla_b200
+    g = torch.Generator().manual_seed(5)
+    B, T, H, K, V = 2, 256, 2, 64, 64
+    q, k, v = (torch.randn(B, T, H, d, generator=g).bfloat16() for d in (K, K, V))
+    mm = torch.clamp(torch.rand(32, 32, generator=g), 1e-5, 1).tril()
+    do = torch.randn(B, T, H, V, generator=g)
+    qc, kc, vc, mc = (t.float().clone().requires_grad_(True) for t in (q, k, v, mm))
+    oracle.causal_chunk_fwd(qc, kc, vc, mc).backward(do)
+    qg, kg, vg = (t.cuda().requires_grad_(True) for t in (q, k, v))
+    mg = mm.cuda().requires_grad_(True)
+    out = mhla_b200.mhla_causal(qg, kg, vg, mg)
+    out.backward(do.cuda().to(out.dtype))
+    for ref, got in ((qc.grad, qg.grad), (kc.grad, kg.grad), (vc.grad, vg.grad), (mc.grad, mg.grad)):
+        assert oracle.err_ratio(ref, got.float().cpu()) < 2e-2

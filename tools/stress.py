@@ -14,6 +14,10 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+# the diagnostics build (time-bounded waits + stall records); MHLA_STRESS_PRODUCT=1 stresses the product build instead
+_DIAG = os.path.join(ROOT, "mhla_b200", "libmhla_b200_diag.so")
+if os.path.exists(_DIAG) and not os.environ.get("MHLA_STRESS_PRODUCT"):
+    os.environ.setdefault("MHLA_B200_LIB", _DIAG)
 import mhla_b200  # noqa: E402
 import oracle  # noqa: E402  (checker)
 from mhla_b200 import _capi  # noqa: E402
