@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MHLA_B200_ABI_VERSION 2
+#define MHLA_B200_ABI_VERSION 3
 
 typedef enum mhla_status {
   MHLA_OK = 0,
@@ -100,6 +100,16 @@ typedef struct mhla_blockmix_desc {
    * (mhla_videogen/diffusion/model/wan/mhla_utils.py:360-362, WanRMSNorm wan/model.py:181-196).  NULL: off. */
   const float* out_rms_weight; /* [D] fp32 device pointer or NULL */
   float out_rms_eps;
+  /* 3-D block view (ABI v3; SURVEY.md 8f rank 1, mhla_videogen/diffusion/model/wan/mhla_utils.py:317-326 and :345-354).
+   * grid = (F, H, W) token grid, layout = (fb, hb, wb) blocks per axis; all zero = block-major tensors as above.
+   * When set, q, k, v, q_rope, k_rope and out are TOKEN-major [B, F*H*W, heads, D] tensors: stride_w is the TOKEN
+   * stride, stride_h the head stride, stride_m is ignored and stride_b must equal F*H*W*stride_w.  Block
+   * j = (fbi*hb + hbi)*wb + wbi covers tokens (fbi*p1 + a, hbi*p2 + b, wbi*p3 + c), in-block order (a, b, c), with
+   * (p1, p2, p3) = (F/fb, H/hb, W/wb); M must equal fb*hb*wb and w = p1*p2*p3.  The kernel gathers every block with one
+   * TMA box per sub-tile and scatters the output the same way, so the reference's five rearrange copies and their
+   * inverse disappear.  Envelope: p2*p3 <= 128 and ceil(p1 / floor(128 / (p2*p3))) <= 2 sub-tiles. */
+  int32_t grid[3];
+  int32_t layout[3];
 } mhla_blockmix_desc;
 
 size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);

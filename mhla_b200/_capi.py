@@ -38,6 +38,7 @@ class BlockmixDesc(C.Structure):
         ("q", Tensor5), ("k", Tensor5), ("v", Tensor5), ("q_rope", Tensor5), ("k_rope", Tensor5), ("out", Tensor5),
         ("mix", C.c_void_p), ("mix_ld", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("out_rms_weight", C.c_void_p), ("out_rms_eps", C.c_float),
+        ("grid", C.c_int32 * 3), ("layout", C.c_int32 * 3),
     ]
 
 
@@ -91,7 +92,7 @@ def lib() -> C.CDLL:
         L.mhla_causal_workspace_bytes.argtypes = [C.POINTER(CausalDesc)]
         L.mhla_fwd_causal.restype = C.c_int
         L.mhla_fwd_causal.argtypes = [C.POINTER(CausalDesc), C.c_void_p]
-        if L.mhla_abi_version() != 2:
+        if L.mhla_abi_version() != 3:
             raise ImportError("libmhla_b200.so ABI version mismatch; rebuild with `python -m mhla_b200.build --force`")
         _lib = L
     return _lib

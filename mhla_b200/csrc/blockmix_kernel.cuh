@@ -89,7 +89,45 @@ struct alignas(64) BlockmixParams {
   int pf_dist;                              // L2 prefetch distance of the producer, in own streaming items (0: off)
   int trace_cta;                            // debug: CTA whose event trace is recorded
   int cnt_stride;                           // words between two dependency counters (padded to separate L2 sectors)
+  // ---- 3-D block view (Wan, blockmix_kernel<D, true>): q,k,v,out are TOKEN-major [B, (F H W), heads, D]; block j =
+  // (fbi, hbi, wbi) of a (fb, hb, wb) layout covers the (p1, p2, p3) sub-grid of tokens, in-block order (p1 p2 p3) as in
+  // mhla_utils.py:317-326.  Rank-5 maps (d, W, H, B*F, heads) with box (64, p3, p2, a, 1) fetch a sub-tile of `a` frames
+  // in ONE TMA box - the reference's rearrange copies (:317-326) and their inverse (:345-354) cost nothing.
+  // tm3[t][0]: box of g3_aper frames, tm3[t][1]: box of the last sub-tile when p1 is not a multiple of g3_aper;
+  // t = 0..5: K(numerator), V, K(normaliser), Q(normaliser), Q(numerator), out.
+  CUtensorMap tm3[6][2];
+  const void* g3_zero;                      // >= 2 KB of zeros (workspace): fills a tile up to a multiple of 16 token rows
+  int g3_F, g3_hb, g3_wb, g3_p1, g3_p2, g3_p3, g3_aper, g3_tail;
+  int g3_rows[2], g3_kpad[2];               // token rows of sub-tile s, and rounded up to the MMA k-step (16)
 };
+
+// 1-D bulk copy global -> shared, completion counted on an mbarrier (bytes multiple of 16, 16-byte aligned addresses)
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// One [rows][64 channels] tile of tensor `which` (0 K, 1 V, 2 Kn, 3 Qn, 4 Qr) for sub-tile `sub` of block j of (b, h).
+template <bool G3D>
+__device__ __forceinline__ void load_tile(const BlockmixParams& p, uint8_t* dst, int which, uint64_t* bar, int c0, int sub,
+                                          int j, int h, int b, uint64_t hint) {
+  if constexpr (!G3D) {
+    tma_load_5d(dst, &p.tmK + which, bar, c0, sub * p.TW, j, h, b, hint);
+  } else {
+    const int wbi = j % p.g3_wb, jj = j / p.g3_wb, hbi = jj % p.g3_hb, fbi = jj / p.g3_hb;
+    const CUtensorMap* tm = &p.tm3[which][(sub == p.nsub - 1) ? p.g3_tail : 0];
+    tma_load_5d(dst, tm, bar, c0, wbi * p.g3_p3, hbi * p.g3_p2, b * p.g3_F + fbi * p.g3_p1 + sub * p.g3_aper, h, hint);
+    const int rows = p.g3_rows[sub], kp = p.g3_kpad[sub];
+    if (kp > rows) bulk_load_1d(dst + rows * 128, p.g3_zero, (uint32_t)(kp - rows) * 128u, bar);   // zero token rows
+  }
+}
+template <bool G3D>
+__device__ __forceinline__ int tile_bytes_of(const BlockmixParams& p, int sub) {
+  if constexpr (!G3D) return p.TW * 128;
+  else return p.g3_kpad[sub] * 128;
+}
 
 // Event trace of CTA 0 (debug): trace[role][item][slot] = clock64, laid out behind the per-CTA counters.
 __device__ __forceinline__ void trace_ev(const BlockmixParams& p, int role, uint32_t item, int slot) {
@@ -211,7 +249,7 @@ __device__ __forceinline__ int p3_stages(const BlockmixParams& p) {
   else return 1 + p.nsub;
 }
 
-template <int D>
+template <int D, bool G3D = false>
 __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_constant__ BlockmixParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -340,30 +378,31 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           const int j = it.t % p.M0;
           for (int sub = 0; sub < p.nsub; ++sub) {
             const int t0 = sub * p.TW;
+            const int tb = tile_bytes_of<G3D>(p, sub);
+            (void)t0;
             if constexpr (D == 64) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
-              tma_load_5d(st, &p.tmK, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
-              tma_load_5d(st + 16384, &p.tmV, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
+              mbar_arrive_expect_tx(&full[r.idx()], 2 * tb);
+              load_tile<G3D>(p, st, 0, &full[r.idx()], 0, sub, j, h, b, kEvictFirst);
+              load_tile<G3D>(p, st + 16384, 1, &full[r.idx()], 0, sub, j, h, b, kEvictFirst);
               r.advance();
             } else {
               for (int kv = 0; kv < 2; ++kv) {
                 mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
                 uint8_t* st = ring + r.idx() * kStageBytes;
-                mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
-                const CUtensorMap* tm = kv ? &p.tmV : &p.tmK;
-                tma_load_5d(st, tm, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
-                tma_load_5d(st + 16384, tm, &full[r.idx()], 64, t0, j, h, b, kEvictFirst);
+                mbar_arrive_expect_tx(&full[r.idx()], 2 * tb);
+                load_tile<G3D>(p, st, kv, &full[r.idx()], 0, sub, j, h, b, kEvictFirst);
+                load_tile<G3D>(p, st + 16384, kv, &full[r.idx()], 64, sub, j, h, b, kEvictFirst);
                 r.advance();
               }
             }
             if (p.ropenorm) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], (D / 64) * tile_bytes);
-              tma_load_5d(st, &p.tmKn, &full[r.idx()], 0, t0, j, h, b, kEvictFirst);
-              if constexpr (D == 128) tma_load_5d(st + 16384, &p.tmKn, &full[r.idx()], 64, t0, j, h, b, kEvictFirst);
+              mbar_arrive_expect_tx(&full[r.idx()], (D / 64) * tb);
+              load_tile<G3D>(p, st, 2, &full[r.idx()], 0, sub, j, h, b, kEvictFirst);
+              if constexpr (D == 128) load_tile<G3D>(p, st + 16384, 2, &full[r.idx()], 64, sub, j, h, b, kEvictFirst);
               r.advance();
             }
           }
@@ -371,17 +410,19 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             if constexpr (D == 64) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], p.nsub * tile_bytes);
+              int qbytes = 0;
+              for (int sub = 0; sub < p.nsub; ++sub) qbytes += tile_bytes_of<G3D>(p, sub);
+              mbar_arrive_expect_tx(&full[r.idx()], qbytes);
               for (int sub = 0; sub < p.nsub; ++sub)
-                tma_load_5d(st + sub * tile_bytes, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, q_hint);
+                load_tile<G3D>(p, st + sub * tile_bytes, 3, &full[r.idx()], 0, sub, j, h, b, q_hint);
               r.advance();
             } else {
               for (int sub = 0; sub < p.nsub; ++sub) {
                 mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
                 uint8_t* st = ring + r.idx() * kStageBytes;
-                mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
-                tma_load_5d(st, &p.tmQn, &full[r.idx()], 0, sub * p.TW, j, h, b, q_hint);
-                tma_load_5d(st + 16384, &p.tmQn, &full[r.idx()], 64, sub * p.TW, j, h, b, q_hint);
+                mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes_of<G3D>(p, sub));
+                load_tile<G3D>(p, st, 3, &full[r.idx()], 0, sub, j, h, b, q_hint);
+                load_tile<G3D>(p, st + 16384, 3, &full[r.idx()], 64, sub, j, h, b, q_hint);
                 r.advance();
               }
             }
@@ -414,13 +455,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (dynamic) wait_dependency();
           const int i = it.t % p.M0;                 // block inside its real group (tensor coordinate)
           const int irow = it.g * p.M + it.t;        // row of the block in the S~ workspace
-          const CUtensorMap* tq = &p.tmQr;
           if constexpr (D == 64) {
             for (int sub = 0; sub < p.nsub; ++sub) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               uint8_t* st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], tile_bytes + (sub == 0 ? 8192 : 0));
-              tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
+              mbar_arrive_expect_tx(&full[r.idx()], tile_bytes_of<G3D>(p, sub) + (sub == 0 ? 8192 : 0));
+              load_tile<G3D>(p, st, 4, &full[r.idx()], 0, sub, i, h, b, kEvictFirst);
               if (sub == 0) tma_load_3d(st + 16384, &p.tmStld, &full[r.idx()], 0, 0, irow, kEvictFirst);
               r.advance();
             }
@@ -434,9 +474,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             for (int sub = 0; sub < p.nsub; ++sub) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               st = ring + r.idx() * kStageBytes;
-              mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes);
-              tma_load_5d(st, tq, &full[r.idx()], 0, sub * p.TW, i, h, b, kEvictFirst);
-              tma_load_5d(st + 16384, tq, &full[r.idx()], 64, sub * p.TW, i, h, b, kEvictFirst);
+              mbar_arrive_expect_tx(&full[r.idx()], 2 * tile_bytes_of<G3D>(p, sub));
+              load_tile<G3D>(p, st, 4, &full[r.idx()], 0, sub, i, h, b, kEvictFirst);
+              load_tile<G3D>(p, st + 16384, 4, &full[r.idx()], 64, sub, i, h, b, kEvictFirst);
               r.advance();
             }
           }
@@ -485,8 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         tc_fence_after();
         trace_ev(p, 1, nitem, 1);
         if (it.type == 1) {
-          const int ksteps = p.TW / 16;
           for (int sub = 0; sub < p.nsub; ++sub) {
+            const int ksteps = G3D ? p.g3_kpad[sub] / 16 : p.TW / 16;
             uint32_t a_addr, b_addr;
             Ring r0 = r;
             if constexpr (D == 64) {
@@ -1066,7 +1106,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #pragma unroll
           for (int sub = 0; sub < 2; ++sub) {
             const int t = sub * p.TW + et;
-            if (sub < p.nsub && et < p.TW && t < p.w) dsum[sub] = __ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps;
+            const bool valid = G3D ? (sub < p.nsub && et < p.g3_rows[sub]) : (sub < p.nsub && et < p.TW && t < p.w);
+            if (valid) dsum[sub] = __ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps;
           }
         }
         mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
@@ -1102,7 +1143,16 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             chunk_tma_begin();
             // the output is never read again: mark its lines evict-first so that they leave L2 before the Q tiles the
             // readout of later groups still needs
-            if (et == 0) tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, ib, h, b, p.o_hint ? kEvictFirst : kEvictNormal);
+            if (et == 0) {
+              const uint64_t oh = p.o_hint ? kEvictFirst : kEvictNormal;
+              if constexpr (!G3D) {
+                tma_store_5d_hint(&p.tmO, buf, c * 64, sub * p.TW, ib, h, b, oh);
+              } else {   // inverse of the block gather (mhla_utils.py:345-354): one box per sub-tile
+                const int wbi = ib % p.g3_wb, jj = ib / p.g3_wb, hbi = jj % p.g3_hb, fbi = jj / p.g3_hb;
+                tma_store_5d_hint(&p.tm3[5][(sub == p.nsub - 1) ? p.g3_tail : 0], buf, c * 64, wbi * p.g3_p3, hbi * p.g3_p2,
+                                  b * p.g3_F + fbi * p.g3_p1 + sub * p.g3_aper, h, oh);
+              }
+            }
             chunk_tma_end();
           }
         }

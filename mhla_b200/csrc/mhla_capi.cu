@@ -106,7 +106,8 @@ const Knobs& knobs() {
 struct BlockmixPlan {
   int G, TW, nsub, wpad, ncols, Mp, n2_rows, n2_cols, n2_scols, kslabs, normalize, ropenorm;
   int pack, Gs, Ms;   // small M: `pack` consecutive groups are scheduled as one group of Ms = pack * M blocks (Gs = G / pack)
-  size_t off_S, off_St, off_den, off_W, off_cnt, total;
+  int g3d, p1, p2, p3, aper, tail, rows[2], kpad[2];   // 3-D block view (desc->grid / layout)
+  size_t off_S, off_St, off_den, off_W, off_cnt, off_zero, total;
 };
 
 int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
@@ -120,6 +121,28 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->G = d->B * d->H;
   pl->TW = d->w >= 128 ? 128 : (d->w + 15) / 16 * 16;
   pl->nsub = (d->w + pl->TW - 1) / pl->TW;
+  pl->g3d = (d->grid[0] | d->grid[1] | d->grid[2] | d->layout[0] | d->layout[1] | d->layout[2]) != 0;
+  pl->tail = 0;
+  pl->rows[0] = pl->rows[1] = pl->kpad[0] = pl->kpad[1] = 0;
+  if (pl->g3d) {
+    const int F = d->grid[0], Hh = d->grid[1], Ww = d->grid[2], fb = d->layout[0], hb = d->layout[1], wb = d->layout[2];
+    if (F < 1 || Hh < 1 || Ww < 1 || fb < 1 || hb < 1 || wb < 1) return MHLA_ERR_INVALID_ARGUMENT;
+    if (F % fb || Hh % hb || Ww % wb) return MHLA_ERR_UNSUPPORTED_SHAPE;
+    pl->p1 = F / fb; pl->p2 = Hh / hb; pl->p3 = Ww / wb;
+    if (d->M != fb * hb * wb || d->w != pl->p1 * pl->p2 * pl->p3) return MHLA_ERR_INVALID_ARGUMENT;
+    if (pl->p2 * pl->p3 > 128 || pl->p2 > 256 || pl->p3 > 256) return MHLA_ERR_UNSUPPORTED_SHAPE;
+    pl->aper = 128 / (pl->p2 * pl->p3);
+    if (pl->aper > pl->p1) pl->aper = pl->p1;
+    pl->TW = 128;
+    pl->nsub = (pl->p1 + pl->aper - 1) / pl->aper;
+    if (pl->nsub > 2) return MHLA_ERR_UNSUPPORTED_SHAPE;
+    for (int sidx = 0; sidx < pl->nsub; ++sidx) {
+      const int a = (sidx == pl->nsub - 1) ? pl->p1 - sidx * pl->aper : pl->aper;
+      pl->rows[sidx] = a * pl->p2 * pl->p3;
+      pl->kpad[sidx] = (pl->rows[sidx] + 15) / 16 * 16;
+    }
+    pl->tail = (pl->p1 % pl->aper) != 0 ? 1 : 0;
+  }
   pl->normalize = (d->flags & MHLA_FLAG_NORMALIZE) ? 1 : 0;
   pl->ropenorm = (pl->normalize && d->k_rope.ptr != nullptr) ? 1 : 0;
   pl->wpad = pl->normalize ? (pl->nsub * pl->TW) : 0;
@@ -128,7 +151,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   // mixing matrix is block-diagonal (pack copies of the caller's matrix).  Their rows are consecutive in the workspace,
   // so nothing else changes; pack must divide the number of groups.
   pl->pack = 1;
-  if (!knobs().no_pack)
+  if (!knobs().no_pack && !pl->g3d)
     for (int pk = 128 / d->M; pk >= 2; --pk)
       if (pl->G % pk == 0) { pl->pack = pk; break; }
   pl->Gs = pl->G / pl->pack;
@@ -146,6 +169,7 @@ int plan_blockmix(const mhla_blockmix_desc* d, BlockmixPlan* pl) {
   pl->off_den = off; off = align_up(off + GM * (pl->wpad ? 2 * pl->wpad : 32) * 4, 1024);
   pl->off_W = off;   off = align_up(off + (size_t)2 * pl->Ms * pl->Mp * 2, 1024);
   pl->off_cnt = off; off = align_up(off + ((size_t)2 * pl->G * kCntStride + 128) * 4, 1024);   // + item tickets, flags
+  pl->off_zero = off; off += 4096;   // zeros (3-D block view: pad rows of a tile); never written by the kernels
   pl->total = off;
   return MHLA_OK;
 }
@@ -198,12 +222,14 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
       d->dtype == MHLA_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   const bool rope = d->k_rope.ptr != nullptr;
 
-  if (!encode_map(&P->tmK, spec_t5(rope ? d->k_rope : d->k, d, pl.TW))) return MHLA_ERR_CUDA;
-  if (!encode_map(&P->tmV, spec_t5(d->v, d, pl.TW))) return MHLA_ERR_CUDA;
-  if (!encode_map(&P->tmKn, spec_t5(d->k, d, pl.TW))) return MHLA_ERR_CUDA;
-  if (!encode_map(&P->tmQn, spec_t5(d->q, d, pl.TW))) return MHLA_ERR_CUDA;
-  if (!encode_map(&P->tmQr, spec_t5(d->q_rope.ptr ? d->q_rope : d->q, d, pl.TW))) return MHLA_ERR_CUDA;
-  if (!encode_map(&P->tmO, spec_t5(d->out, d, pl.TW))) return MHLA_ERR_CUDA;
+  if (!pl.g3d) {
+    if (!encode_map(&P->tmK, spec_t5(rope ? d->k_rope : d->k, d, pl.TW))) return MHLA_ERR_CUDA;
+    if (!encode_map(&P->tmV, spec_t5(d->v, d, pl.TW))) return MHLA_ERR_CUDA;
+    if (!encode_map(&P->tmKn, spec_t5(d->k, d, pl.TW))) return MHLA_ERR_CUDA;
+    if (!encode_map(&P->tmQn, spec_t5(d->q, d, pl.TW))) return MHLA_ERR_CUDA;
+    if (!encode_map(&P->tmQr, spec_t5(d->q_rope.ptr ? d->q_rope : d->q, d, pl.TW))) return MHLA_ERR_CUDA;
+    if (!encode_map(&P->tmO, spec_t5(d->out, d, pl.TW))) return MHLA_ERR_CUDA;
+  }
   {
     MapSpec s{dt16, 3, S, {(uint64_t)D, (uint64_t)D, GM}, {(uint64_t)D * 2, (uint64_t)pl.ncols * 2},
               {64, (uint32_t)D, 1}};
@@ -235,6 +261,25 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
               {64, (uint32_t)D, 1}};
     if (!encode_map(&P->tmStld, s)) return MHLA_ERR_CUDA;
   }
+  if (pl.g3d) {
+    // token-major [B, F*H*W, heads, D] viewed as (d, W, H, B*F, heads); one box = (64 channels, p3, p2, a frames, 1 head)
+    const mhla_tensor5* ts[6] = {rope ? &d->k_rope : &d->k, &d->v, &d->k, &d->q, d->q_rope.ptr ? &d->q_rope : &d->q, &d->out};
+    const uint64_t F = d->grid[0], Hh = d->grid[1], Ww = d->grid[2];
+    for (int t = 0; t < 6; ++t) {
+      const uint64_t tok = (uint64_t)ts[t]->stride_w * 2;
+      for (int v = 0; v < 2; ++v) {
+        const uint32_t a = v == 0 ? (uint32_t)pl.aper : (uint32_t)(pl.p1 - (pl.nsub - 1) * pl.aper);
+        MapSpec s{dt16, 5, const_cast<void*>(ts[t]->ptr), {(uint64_t)D, Ww, Hh, (uint64_t)d->B * F, (uint64_t)d->H},
+                  {tok, tok * Ww, tok * Ww * Hh, (uint64_t)ts[t]->stride_h * 2}, {64, (uint32_t)pl.p3, (uint32_t)pl.p2, a, 1}};
+        if (d->H == 1) s.strides[3] = tok * Ww * Hh * (uint64_t)d->B * F;   // a valid stand-in for the size-1 dimension
+        if (!encode_map(&P->tm3[t][v], s)) return MHLA_ERR_CUDA;
+      }
+    }
+    P->g3_zero = ws + pl.off_zero;
+    P->g3_F = d->grid[0]; P->g3_hb = d->layout[1]; P->g3_wb = d->layout[2];
+    P->g3_p1 = pl.p1; P->g3_p2 = pl.p2; P->g3_p3 = pl.p3; P->g3_aper = pl.aper; P->g3_tail = pl.tail;
+    for (int i = 0; i < 2; ++i) { P->g3_rows[i] = pl.rows[i]; P->g3_kpad[i] = pl.kpad[i]; }
+  }
   P->ws_S = S;
   P->ws_St = reinterpret_cast<uint16_t*>(St);
   P->den = den;
@@ -258,7 +303,7 @@ unsigned long long* g_prof_buffer = nullptr;   // debug: per-CTA role counters (
 constexpr int kMaxDevices = 64;
 struct DeviceState {
   int sms = 0;          // 0: not queried yet; < 0: not an sm_100 device
-  bool attr64 = false, attr128 = false, attr_smalln = false;
+  bool attr64 = false, attr128 = false, attr64g = false, attr128g = false, attr_smalln = false;
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -290,6 +335,7 @@ std::vector<SmallNCacheEntry> g_smalln_cache;
 bool smalln_eligible(const mhla_blockmix_desc* d) {
   if (d->D != 64 || d->M > mhla::kSnMaxM || (long long)d->M * d->w > mhla::kSnRows) return false;
   if (d->q_rope.ptr || d->k_rope.ptr || d->out_rms_weight) return false;
+  if (d->grid[0] | d->grid[1] | d->grid[2] | d->layout[0] | d->layout[1] | d->layout[2]) return false;
   if (d->flags & (MHLA_FLAG_NO_SMALLN | MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH | MHLA_FLAG_FUSED | MHLA_FLAG_STOP_AFTER_P1 |
                   MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2))
     return false;
@@ -404,6 +450,12 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (!t5_ok(d->q) || !t5_ok(d->k) || !t5_ok(d->v) || !t5_ok(d->out)) return MHLA_ERR_ALIGNMENT;
   if (d->q_rope.ptr && (!t5_ok(d->q_rope) || !t5_ok(d->k_rope))) return MHLA_ERR_ALIGNMENT;
   if (d->mix_ld < d->M) return MHLA_ERR_INVALID_ARGUMENT;
+  if (pl.g3d) {   // token-major tensors: the batch must follow the token axis directly ((b, f) is ONE tensor-map dimension)
+    const long long ntok = (long long)d->grid[0] * d->grid[1] * d->grid[2];
+    const mhla_tensor5* ts[6] = {&d->q, &d->k, &d->v, &d->out, &d->q_rope, &d->k_rope};
+    for (const mhla_tensor5* t : ts)
+      if (t->ptr && d->B > 1 && t->stride_b != ntok * t->stride_w) return MHLA_ERR_ALIGNMENT;
+  }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   DeviceState* dst = nullptr;
   rc = device_state(&dst);
@@ -437,10 +489,11 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.o_hint = kn.o_hint;
   P.q_hint = kn.q_hint;
   P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = 0;   // (round-1 tuning options, fixed at their best values)
-  auto kern = d->D == 64 ? mhla::blockmix_kernel<64> : mhla::blockmix_kernel<128>;
+  auto kern = pl.g3d ? (d->D == 64 ? mhla::blockmix_kernel<64, true> : mhla::blockmix_kernel<128, true>)
+                     : (d->D == 64 ? mhla::blockmix_kernel<64, false> : mhla::blockmix_kernel<128, false>);
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    bool& attr = d->D == 64 ? dst->attr64 : dst->attr128;
+    bool& attr = pl.g3d ? (d->D == 64 ? dst->attr64g : dst->attr128g) : (d->D == 64 ? dst->attr64 : dst->attr128);
     if (!attr) {
       if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
                    "cudaFuncSetAttribute"))
@@ -454,6 +507,9 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   const bool dbg_phase = (d->flags & (MHLA_FLAG_STOP_AFTER_P1 | MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2)) != 0;
   const bool single = (d->flags & MHLA_FLAG_FUSED) || !(dbg_phase || (d->flags & (MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH)));
   P.self_prep = (single && (d->flags & MHLA_FLAG_WS_PERSISTENT) && !kn.no_self_prep) ? 1 : 0;
+  if (!P.self_prep && pl.g3d &&
+      !cuda_ok(cudaMemsetAsync(static_cast<uint8_t*>(d->workspace) + pl.off_zero, 0, 4096, stream), "cudaMemsetAsync(zero rows)"))
+    return MHLA_ERR_CUDA;
   if (!P.self_prep) {
     mhla::prep_mix_scaled_kernel<<<16, 1024, 0, stream>>>(d->mix, (long long)d->mix_ld,
                                                        reinterpret_cast<uint16_t*>(ws + pl.off_W), pl.Ms, pl.Mp, d->M,

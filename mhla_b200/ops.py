@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -240,6 +240,79 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         if in_dtype != cdtype:
             res = res.to(in_dtype)
     return res
+
+
+def mhla_blockmix_grid(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
+                       out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None,
+                       out_rms_eps: float = 1e-6, three_launch: bool = False) -> torch.Tensor:
+    """Block-mixed MHLA forward on TOKEN-major tensors with a 3-D block structure (variant B, Wan): q, k, v (and the
+    roped copies) are [B, F*H*W, heads, D] - e.g. plain views of the q/k/v projections - and ``layout = (fb, hb, wb)``
+    cuts the ``grid = (F, H, W)`` token grid into M = fb*hb*wb blocks of (F/fb)*(H/hb)*(W/wb) tokens, exactly the
+    ``"b (fb p1 hb p2 wb p3) h c -> (b h) (fb hb wb) (p1 p2 p3) c"`` rearrangement of mhla_utils.py:317-326.  The kernel
+    gathers the blocks with TMA boxes and scatters the output back (:345-354), so no block-major copy is ever made.
+    Returns [B, F*H*W, heads, D].  Inference path (no autograd graph)."""
+    _require_cuda(q, k, v, mix, q_rope, k_rope)
+    if (q_rope is None) != (k_rope is None):
+        raise ValueError("q_rope and k_rope must be given together")
+    F_, H_, W_ = (int(x) for x in grid)
+    fb, hb, wb = (int(x) for x in layout)
+    B, N, nh, D = q.shape
+    if N != F_ * H_ * W_:
+        raise ValueError(f"q has {N} tokens, grid {grid} has {F_ * H_ * W_}")
+    if D not in (64, 128):
+        raise ValueError("the 3-D block view needs a head dim of 64 or 128")
+    M, w = fb * hb * wb, (F_ // fb) * (H_ // hb) * (W_ // wb)
+    cdtype = q.dtype if q.dtype in _DT else torch.bfloat16
+
+    def prep(t):
+        if t is None:
+            return None
+        t = t.detach()
+        if tuple(t.shape) != (B, N, nh, D):
+            raise ValueError(f"expected a [{B}, {N}, {nh}, {D}] tensor, got {tuple(t.shape)}")
+        if t.dtype != cdtype:
+            t = t.to(cdtype)
+        ok = (t.stride(-1) == 1 and t.data_ptr() % 16 == 0 and t.stride(1) % 8 == 0 and t.stride(2) % 8 == 0 and
+              (B == 1 or t.stride(0) == N * t.stride(1)))
+        return t if ok else t.contiguous()
+
+    q4, k4, v4, qr4, kr4 = prep(q), prep(k), prep(v), prep(q_rope), prep(k_rope)
+    o4 = torch.empty((B, N, nh, D), dtype=cdtype, device=q.device) if out is None else out
+    if out is not None and (o4.dtype != cdtype or tuple(o4.shape) != (B, N, nh, D) or prep(o4) is not o4):
+        raise ValueError("out must be a [B, N, heads, D] tensor of the compute dtype with TMA-compatible strides")
+    mix2 = mix.detach().reshape(mix.shape[0], mix.shape[1]).to(torch.float32).contiguous()
+    if tuple(mix2.shape) != (M, M):
+        raise ValueError(f"mix must be [{M}, {M}], got {tuple(mix.shape)}")
+    t5 = lambda t: _capi.Tensor5(None, 0, 0, 0, 0) if t is None else _capi.Tensor5(t.data_ptr(), t.stride(0), t.stride(2), 0, t.stride(1))  # noqa: E731
+    flags = (_capi.FLAG_NORMALIZE if normalize else 0) | (_capi.FLAG_UNFUSED if three_launch else _capi.FLAG_WS_PERSISTENT)
+    L = _capi.lib()
+    d = _capi.BlockmixDesc()
+    d.B, d.H, d.M, d.w, d.D = B, nh, M, w, D
+    d.dtype, d.flags, d.eps = _DT[cdtype], flags, float(eps)
+    d.grid[0], d.grid[1], d.grid[2] = F_, H_, W_
+    d.layout[0], d.layout[1], d.layout[2] = fb, hb, wb
+    nbytes = L.mhla_blockmix_workspace_bytes(C.byref(d))
+    if nbytes == 0:
+        raise _capi.MhlaError(f"unsupported 3-D block view: grid {tuple(grid)} layout {tuple(layout)} D={D} "
+                              "(needs p2*p3 <= 128 and at most two sub-tiles per block)")
+    lay = (C.c_size_t * 8)()
+    _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
+    d.q, d.k, d.v, d.out, d.q_rope, d.k_rope = t5(q4), t5(k4), t5(v4), t5(o4), t5(qr4), t5(kr4)
+    d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
+    rms_w = None
+    if out_rms_weight is not None:
+        rms_w = out_rms_weight.detach().to(device=q.device, dtype=torch.float32).contiguous()
+    d.out_rms_weight, d.out_rms_eps = (rms_w.data_ptr() if rms_w is not None else None), float(out_rms_eps)
+    stream = torch.cuda.current_stream(q.device)
+    sig = ("grid", B, nh, F_, H_, W_, fb, hb, wb, D, cdtype, flags, qr4 is not None)
+    if three_launch:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    else:
+        ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig, int(lay[4]))
+    d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
+    with torch.cuda.device(q.device):
+        _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
+    return o4
 
 
 _HOST_STREAMS: "dict[int, tuple]" = {}

@@ -283,3 +283,49 @@ def test_cuda_graph_capture_of_a_dit_stack():
     g2.replay()
     torch.cuda.synchronize()
     assert torch.equal(og, ref)
+
+
+@pytest.mark.parametrize("B,nh,D,grid,layout,normalize,rope", [
+    (2, 2, 64, (2, 4, 8), (1, 2, 2), False, True),       # the b_nonorm fixture's geometry: 4 blocks of 16 tokens
+    (1, 3, 128, (6, 10, 20), (3, 5, 10), False, True),   # Wan-like: 150 blocks of 2*2*2 = 8 tokens
+    (1, 2, 128, (7, 12, 10), (1, 2, 2), True, True),     # Wan's block shape: 7*6*5 = 210 tokens (two sub-tiles, ragged tail)
+    (2, 2, 128, (14, 6, 10), (2, 1, 2), True, True),     # batch 2 (the (b, f) axis of the tensor map), 7*6*5 tokens
+    (1, 2, 64, (8, 4, 4), (2, 2, 2), True, False),       # 4*2*2 = 16 tokens, no rope, D = 64
+    (1, 1, 64, (3, 8, 16), (1, 1, 1), True, False),      # one block of 3*8*16 = 384 tokens? no: exceeds 256 -> see below
+])
+@pytest.mark.parametrize("three_launch", [False, True])
+def test_blockmix_3d_block_view(B, nh, D, grid, layout, normalize, rope, three_launch):
+    """Token-major [B, N, heads, D] tensors consumed in place through the 3-D block TMA view against the oracle on the
+    rearranged (block-major) tensors - the reference's own layout transformation, mhla_utils.py:317-326 / :345-354."""
+    import mhla_b200
+    from einops import rearrange
+    F_, H_, W_ = grid
+    fb, hb, wb = layout
+    p1, p2, p3 = F_ // fb, H_ // hb, W_ // wb
+    N, M, w = F_ * H_ * W_, fb * hb * wb, p1 * p2 * p3
+    g = torch.Generator().manual_seed(7)
+    mk = lambda relu: ((torch.relu(torch.randn(B, N, nh, D, generator=g)) + 1e-6) if relu  # noqa: E731
+                       else torch.randn(B, N, nh, D, generator=g)).bfloat16()
+    q, k, v = mk(True), mk(True), mk(False)
+    qr, kr = (mk(False), mk(False)) if rope else (None, None)
+    W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
+    cu = lambda t: None if t is None else t.cuda()  # noqa: E731
+    if w > 256:
+        with pytest.raises(Exception):
+            mhla_b200.mhla_blockmix_grid(cu(q), cu(k), cu(v), W.cuda(), grid, layout, normalize=normalize)
+        return
+    out = mhla_b200.mhla_blockmix_grid(cu(q), cu(k), cu(v), W.cuda(), grid, layout, q_rope=cu(qr), k_rope=cu(kr),
+                                       normalize=normalize, three_launch=three_launch)
+    torch.cuda.synchronize()
+    pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
+    kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
+    blk = lambda t: None if t is None else rearrange(t, pat, **kw)  # noqa: E731
+    ref = oracle.blockmix_fwd(blk(q), blk(k), blk(v), W, normalize=normalize, q_rope=blk(qr), k_rope=blk(kr))
+    ref = rearrange(ref, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw)
+    _check(ref, out, torch.bfloat16)
+    # strided views of one fused [B, N, 3, heads, D] projection output are consumed in place as well
+    if not rope:
+        qkv = torch.stack([q, k, v], dim=2).cuda()
+        out2 = mhla_b200.mhla_blockmix_grid(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], W.cuda(), grid, layout,
+                                            normalize=normalize, three_launch=three_launch)
+        assert torch.equal(out2, out)
