@@ -268,6 +268,7 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--graph", action="store_true", help="replay CUDA graphs also below 4 ranks")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
     args = ap.parse_args()
@@ -342,7 +343,9 @@ def main():
     if not err < 5e-3:
         raise SystemExit(f"bench self-check failed: err_ratio {err}")
     it[0] = 0
-    if not args.no_graph:
+    # (graph replays pay ~1.5 us per step for the lost PDL overlap between consecutive launches: only worth it once the
+    #  per-rank kernel is as short as the ~25 us Python enqueue, i.e. from 4 ranks on)
+    if not args.no_graph and (world >= 4 or args.graph):
         try:
             for i in range(nsets):
                 launch(i)                                  # warm every set's descriptors / workspace

@@ -152,6 +152,29 @@ typedef struct mhla_causal_desc {
 } mhla_causal_desc;
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc);
+
+/*
+ * Fused pre-processing of the Wan MHLA layer (mhla_videogen/diffusion/model/wan/mhla_utils.py:267-276, :127-156,
+ * :303-316): per token row  y = relu(x * rsqrt(mean_C(x^2) + eps_norm) * w) + eps  (WanRMSNorm over the FULL channel
+ * dim, wan/model.py:181-196), then the 3-axis RoPE as a rotation of the interleaved pairs (2i, 2i+1) of every head by
+ * the angle table [N, D/2] (cos, sin of the reference's complex128 freqs gathered for the (F, H, W) token grid).
+ * Writes the roped q, k - and the un-roped ones when q_plain / k_plain are given (normaliser operands) - token-major
+ * [B*N, C] in the 16-bit dtype: the layout the 3-D block view of mhla_fwd_blockmix consumes.  One launch.
+ */
+typedef struct mhla_wan_prep_desc {
+  int32_t rows, N, C, D;        /* rows = B*N token rows, N tokens per sample, C = heads*D channels, D head dim */
+  int32_t in_dtype;             /* 0 bf16, 1 fp16, 2 fp32 (the q / k projection outputs) */
+  int32_t out_dtype;            /* mhla_dtype */
+  const void* xq; const void* xk;   /* [rows, C], row pitch ld_in elements */
+  int64_t ld_in;
+  void* q_rope; void* k_rope;   /* [rows, C] 16-bit, contiguous */
+  void* q_plain; void* k_plain; /* optional un-roped outputs, NULL to skip */
+  const float* wq; const float* wk; /* RMSNorm weights [C] fp32, NULL = no normalisation */
+  const float* cos_table; const float* sin_table; /* [N, D/2] fp32, NULL = no RoPE */
+  float eps_norm, eps;
+} mhla_wan_prep_desc;
+
+int mhla_wan_prep(const mhla_wan_prep_desc* desc, void* stream);
 int mhla_fwd_causal(const mhla_causal_desc* desc, void* stream);
 
 /* Misc. */

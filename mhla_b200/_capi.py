@@ -22,7 +22,7 @@ FLAG_NO_SMALLN = 1 << 15
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
-    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal", "mhla_wan_prep",
 ]
 
 
@@ -53,6 +53,17 @@ class CausalDesc(C.Structure):
         ("q", Tensor4), ("k", Tensor4), ("v", Tensor4), ("out", Tensor4),
         ("mm", C.c_void_p), ("mm_ld", C.c_int64), ("L", C.c_int32),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+class WanPrepDesc(C.Structure):
+    _fields_ = [
+        ("rows", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("D", C.c_int32),
+        ("in_dtype", C.c_int32), ("out_dtype", C.c_int32),
+        ("xq", C.c_void_p), ("xk", C.c_void_p), ("ld_in", C.c_int64),
+        ("q_rope", C.c_void_p), ("k_rope", C.c_void_p), ("q_plain", C.c_void_p), ("k_plain", C.c_void_p),
+        ("wq", C.c_void_p), ("wk", C.c_void_p), ("cos_table", C.c_void_p), ("sin_table", C.c_void_p),
+        ("eps_norm", C.c_float), ("eps", C.c_float),
     ]
 
 
@@ -90,6 +101,9 @@ def lib() -> C.CDLL:
         L.mhla_blockmix_workspace_init.argtypes = [C.POINTER(BlockmixDesc), C.c_void_p]
         L.mhla_causal_workspace_bytes.restype = C.c_size_t
         L.mhla_causal_workspace_bytes.argtypes = [C.POINTER(CausalDesc)]
+        if hasattr(L, "mhla_wan_prep"):
+            L.mhla_wan_prep.restype = C.c_int
+            L.mhla_wan_prep.argtypes = [C.POINTER(WanPrepDesc), C.c_void_p]
         L.mhla_fwd_causal.restype = C.c_int
         L.mhla_fwd_causal.argtypes = [C.POINTER(CausalDesc), C.c_void_p]
         if L.mhla_abi_version() != 3:

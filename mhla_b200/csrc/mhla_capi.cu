@@ -15,6 +15,7 @@
 #include "blockmix_kernel.cuh"
 #include "causal_kernel.cuh"
 #include "smalln_kernel.cuh"
+#include "wan_prep_kernel.cuh"
 
 namespace {
 
@@ -596,6 +597,33 @@ namespace { __global__ void stall_selftest_kernel() { mhla::report_stall_diag(99
 int mhla_debug_trigger_stall(void* stream_) {
   stall_selftest_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream_)>>>();
   return cuda_ok(cudaGetLastError(), "stall_selftest_kernel") ? MHLA_OK : MHLA_ERR_CUDA;
+}
+
+int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
+  if (!d || !d->xq || !d->xk || !d->q_rope || !d->k_rope) return MHLA_ERR_INVALID_ARGUMENT;
+  if ((d->q_plain == nullptr) != (d->k_plain == nullptr) || (d->cos_table == nullptr) != (d->sin_table == nullptr))
+    return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->rows < 1 || d->N < 1 || d->C < 8 || d->C % 8 || d->D < 8 || d->D % 8 || d->C % d->D || d->C > 8192)
+    return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->in_dtype < 0 || d->in_dtype > 2 || (d->out_dtype != MHLA_BF16 && d->out_dtype != MHLA_FP16)) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->xq) | reinterpret_cast<uintptr_t>(d->xk) |
+                       reinterpret_cast<uintptr_t>(d->q_rope) | reinterpret_cast<uintptr_t>(d->k_rope) |
+                       reinterpret_cast<uintptr_t>(d->q_plain) | reinterpret_cast<uintptr_t>(d->k_plain) |
+                       reinterpret_cast<uintptr_t>(d->cos_table) | reinterpret_cast<uintptr_t>(d->sin_table);
+  if ((al & 15) != 0 || d->ld_in % 8 != 0 || (d->D / 2) % 4 != 0) return MHLA_ERR_ALIGNMENT;
+  mhla::WanPrepParams P{};
+  P.xq = d->xq; P.xk = d->xk; P.q_rope = d->q_rope; P.k_rope = d->k_rope; P.q_plain = d->q_plain; P.k_plain = d->k_plain;
+  P.wq = d->wq; P.wk = d->wk; P.cos_t = d->cos_table; P.sin_t = d->sin_table; P.ld_in = d->ld_in;
+  P.rows = d->rows; P.N = d->N; P.C = d->C; P.D = d->D; P.in_dtype = d->in_dtype; P.out_fp16 = d->out_dtype == MHLA_FP16;
+  P.eps_norm = d->eps_norm; P.eps = d->eps;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int threads = ((d->C / 8) + 31) / 32 * 32;
+  if (d->in_dtype == 0) mhla::wan_prep_kernel<0><<<d->rows, threads, 0, stream>>>(P);
+  else if (d->in_dtype == 1) mhla::wan_prep_kernel<1><<<d->rows, threads, 0, stream>>>(P);
+  else mhla::wan_prep_kernel<2><<<d->rows, threads, 0, stream>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "wan_prep_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
 }
 
 size_t mhla_causal_workspace_bytes(const mhla_causal_desc* desc) { return mhla::causal_workspace_bytes(desc); }

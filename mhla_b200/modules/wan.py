@@ -16,7 +16,7 @@ from einops import rearrange
 from torch import nn
 
 from ..mixing import BlockDistanceConv3D
-from ..ops import mhla_blockmix
+from ..ops import mhla_blockmix, mhla_blockmix_grid, wan_prep
 
 
 class WanRMSNorm(nn.Module):
@@ -110,6 +110,7 @@ class _MHLAVideoBase(nn.Module):
             self.g_norm = WanRMSNorm(dim if self._gnorm == "dim" else dim_head, eps=eps)
         self.is_gated = gated
         self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: per-head g_norm inside the kernel epilogue
+        self.fast_path = kwargs.get("fast_path", True)           # extension: fused pre-processing + 3-D block TMA view
         self.is_lepe = lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
@@ -148,6 +149,42 @@ class _MHLAVideoBase(nn.Module):
                 nn.init.zeros_(param)
         return model
 
+    def _forward_fused(self, x, q, k, v, lepe, grid, grid_sizes, freqs):
+        """Inference path without a single layout copy: ONE pre-processing launch (RMSNorm over C, relu + eps, RoPE,
+        16-bit token-major outputs: csrc/wan_prep_kernel.cuh) and ONE operator launch that gathers the 3-D blocks by
+        TMA and scatters the output back (csrc/blockmix_kernel.cuh, 3-D block view) - instead of .float() copies, a
+        complex128 RoPE with a host sync, a 5-tensor cat and two rearranges (mhla_utils.py:303-326, :345-354)."""
+        B, N, C = x.shape
+        nh, D = self.num_heads, self.head_dim
+        cos, sin = _rope_tables(grid, freqs, x.device)
+        wq = self.norm_q.weight if isinstance(self.norm_q, WanRMSNorm) else None
+        wk = self.norm_k.weight if isinstance(self.norm_k, WanRMSNorm) else None
+        eps_n = self.norm_q.eps if isinstance(self.norm_q, WanRMSNorm) else 1e-6
+        q_rope, k_rope, q_n, k_n = wan_prep(q, k, wq, wk, cos, sin, D, eps_norm=eps_n, eps=self.eps,
+                                            want_plain=self.normalize_out)
+        cdtype = q_rope.dtype
+        v4 = (v if v.dtype == cdtype else v.to(cdtype)).view(B, N, nh, D)
+        fuse = (dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps)
+                if (self._gnorm == "head" and self.fuse_out_norm) else {})
+        Wm = self.block_attn.conv.weight
+        if self.normalize_out:
+            out = mhla_blockmix_grid(q_n, k_n, v4, Wm, grid, self.blocks_layout, q_rope=q_rope, k_rope=k_rope, eps=self.eps,
+                                     normalize=True, **fuse)
+        else:
+            out = mhla_blockmix_grid(q_rope, k_rope, v4, Wm, grid, self.blocks_layout, eps=self.eps, normalize=False, **fuse)
+        out = out.to(q.dtype)
+        if self._gnorm == "head" and not fuse:
+            out = self.g_norm(out)
+        out = out.reshape(B, N, C)
+        if self._gnorm == "dim":
+            out = self.g_norm(out)
+        if self.is_gated:
+            out = out * self.g_fn(self.g(x))
+        if self.is_lepe:
+            out = out + lepe
+        out = self.o(out)
+        return self.out_rmsnorm(out) if self._out_norm else out
+
     def forward(self, x: torch.Tensor, seq_lens, grid_sizes, freqs) -> torch.Tensor:
         B, N, C = x.shape
         g0 = grid_sizes[0]
@@ -162,6 +199,11 @@ class _MHLAVideoBase(nn.Module):
             lepe = self.lepe(rearrange(v, "b (f h w) c -> b c f h w", f=F_, h=H_, w=W_))
             lepe = rearrange(lepe, "b c f h w -> b (f h w) c")
         dtype = q.dtype
+        W = self.block_attn.conv.weight
+        training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)
+        if (self.fast_path and not training and x.is_cuda and D in (64, 128) and N == F_ * H_ * W_ and p2 * p3 <= 128
+                and -(-p1 // max(1, min(p1, 128 // (p2 * p3)))) <= 2):
+            return self._forward_fused(x, q, k, v, lepe, (F_, H_, W_), grid_sizes, freqs)
         q = torch.relu(self.norm_q(q.float())) + self.eps                          # :308, 267-276
         k = torch.relu(self.norm_k(k.float())) + self.eps
         q, k, v = (t.view(B, N, nh, D) for t in (q, k, v))
@@ -171,8 +213,6 @@ class _MHLAVideoBase(nn.Module):
         pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
         kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
         blk = lambda t: rearrange(t.to(cdtype), pat, **kw).contiguous()           # noqa: E731  (:317-326, one 16-bit copy each)
-        W = self.block_attn.conv.weight
-        training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)
         # the per-head g_norm (:360-364) is fused into the kernel's readout epilogue (fp32, before the single rounding)
         fuse_norm = self._gnorm == "head" and self.fuse_out_norm and not training and D in (64, 128)
         fuse = dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps) if fuse_norm else {}

@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -313,6 +313,44 @@ def mhla_blockmix_grid(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, 
     with torch.cuda.device(q.device):
         _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
     return o4
+
+
+def wan_prep(xq: torch.Tensor, xk: torch.Tensor, wq: Optional[torch.Tensor], wk: Optional[torch.Tensor], cos: Optional[torch.Tensor],
+             sin: Optional[torch.Tensor], head_dim: int, *, eps_norm: float = 1e-6, eps: float = 1e-6, want_plain: bool = False,
+             out_dtype: Optional[torch.dtype] = None):
+    """Fused Wan pre-processing (one launch, csrc/wan_prep_kernel.cuh): xq, xk [B, N, C] projection outputs (bf16 / fp16 /
+    fp32) -> relu(rmsnorm_C(x) * w) + eps, RoPE by the [N, D/2] cos / sin tables, written token-major in 16 bit.
+    Returns (q_rope, k_rope, q_plain, k_plain) as [B, N, heads, D] views; the plain pair is None unless ``want_plain``.
+    Replaces mhla_utils.py:267-276 + :127-156 + :303-316 (fp32 / complex128 temporaries, ~10 launches, a host sync)."""
+    _require_cuda(xq, xk, wq, wk, cos, sin)
+    B, N, Cc = xq.shape
+    D = int(head_dim)
+    in_code = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[xq.dtype]
+    odt = out_dtype or (torch.float16 if xq.dtype == torch.float16 else torch.bfloat16)
+    xq2 = xq.detach().reshape(B * N, Cc)
+    xk2 = xk.detach().to(xq.dtype).reshape(B * N, Cc)
+    if xq2.stride(1) != 1 or xq2.stride(0) % 8:
+        xq2 = xq2.contiguous()
+    if xk2.stride(1) != 1 or xk2.stride(0) != xq2.stride(0):
+        xk2 = xk2.contiguous()
+        xq2 = xq2.contiguous()
+    mk = lambda: torch.empty((B, N, Cc // D, D), dtype=odt, device=xq.device)  # noqa: E731
+    qr, kr = mk(), mk()
+    qp, kp = (mk(), mk()) if want_plain else (None, None)
+    f32 = lambda t: None if t is None else t.detach().to(device=xq.device, dtype=torch.float32).contiguous()  # noqa: E731
+    wq, wk, cos, sin = f32(wq), f32(wk), f32(cos), f32(sin)
+    d = _capi.WanPrepDesc()
+    d.rows, d.N, d.C, d.D = B * N, N, Cc, D
+    d.in_dtype, d.out_dtype = in_code, _DT[odt]
+    d.xq, d.xk, d.ld_in = xq2.data_ptr(), xk2.data_ptr(), xq2.stride(0)
+    d.q_rope, d.k_rope = qr.data_ptr(), kr.data_ptr()
+    d.q_plain, d.k_plain = (qp.data_ptr(), kp.data_ptr()) if want_plain else (None, None)
+    d.wq, d.wk = (wq.data_ptr() if wq is not None else None), (wk.data_ptr() if wk is not None else None)
+    d.cos_table, d.sin_table = (cos.data_ptr(), sin.data_ptr()) if cos is not None else (None, None)
+    d.eps_norm, d.eps = float(eps_norm), float(eps)
+    with torch.cuda.device(xq.device):
+        _capi.check(_capi.lib().mhla_wan_prep(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_wan_prep")
+    return qr, kr, qp, kp
 
 
 _HOST_STREAMS: "dict[int, tuple]" = {}

@@ -181,3 +181,58 @@ def test_dit_module_accepts_3d_tokens():
         y3 = m(x.flatten(1, 2))
     assert y3.shape == (x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
     torch.testing.assert_close(y3.view_as(y4), y4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("in_dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("plain", [False, True])
+def test_wan_prep_kernel_matches_reference_preprocessing(in_dtype, plain):
+    """csrc/wan_prep_kernel.cuh against the reference sequence: WanRMSNorm over the full channel dim (wan/model.py:181-196),
+    relu + eps (mhla_utils.py:267-276), complex RoPE on interleaved pairs (:127-156; oracle.rope_apply_wan)."""
+    import mhla_b200
+    from mhla_b200.modules.wan import _rope_tables
+    torch.manual_seed(0)
+    B, grid, nh, D = 2, (3, 4, 6), 3, 64
+    N, Cc = grid[0] * grid[1] * grid[2], nh * D
+    xq, xk = torch.randn(B, N, Cc), torch.randn(B, N, Cc)
+    wq, wk = 1 + 0.1 * torch.randn(Cc), 1 + 0.1 * torch.randn(Cc)
+    freqs = oracle.rope_freqs_wan(D)
+    xq_, xk_ = xq.to(in_dtype), xk.to(in_dtype)
+
+    def ref(x, w):
+        xf = x.float()
+        y = torch.relu(xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-6) * w) + 1e-6
+        y = y.view(B, N, nh, D)
+        return y, oracle.rope_apply_wan(y, grid, freqs)
+
+    (qp_ref, qr_ref), (kp_ref, kr_ref) = ref(xq_, wq), ref(xk_, wk)
+    cos, sin = _rope_tables(grid, freqs, torch.device("cuda"))
+    qr, kr, qp, kp = mhla_b200.wan_prep(xq_.cuda(), xk_.cuda(), wq.cuda(), wk.cuda(), cos, sin, D, want_plain=plain)
+    torch.cuda.synchronize()
+    assert qr.dtype == torch.bfloat16 and tuple(qr.shape) == (B, N, nh, D)
+    for got, want in ((qr, qr_ref), (kr, kr_ref)) + (((qp, qp_ref), (kp, kp_ref)) if plain else ()):
+        assert oracle.err_ratio(want, got.float().cpu()) < 3e-3           # bf16 output rounding (2^-9)
+    if not plain:
+        assert qp is None and kp is None
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalize_out,gated,lepe", [(False, False, False), (True, True, False), (True, False, True)])
+def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated, lepe):
+    """MHLA_Video_Uni at Wan's block shape (7*6*5 = 210 tokens per block, D = 128): the fused inference path (one
+    pre-processing launch + the 3-D block view) against the module's own reference-style path (torch pre-processing +
+    block-major rearrange copies), bf16 autocast as in the reference's sampler (inference.py:284)."""
+    torch.manual_seed(3)
+    dim, heads, layout, grid = 256, 2, (1, 2, 2), (7, 12, 10)
+    N = grid[0] * grid[1] * grid[2]
+    m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=normalize_out, is_gated=gated,
+                       is_lepe=lepe).cuda().eval()
+    m.block_attn.conv.weight.data.mul_(1.0 + 0.1 * torch.rand_like(m.block_attn.conv.weight))
+    x = torch.randn(2, N, dim, device="cuda")
+    gs = torch.tensor([list(grid)] * 2, dtype=torch.long)
+    freqs = oracle.rope_freqs_wan(dim // heads)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        y_fast = m(x, torch.tensor([N, N]), gs, freqs)
+        m.fast_path = False
+        y_slow = m(x, torch.tensor([N, N]), gs, freqs)
+    assert oracle.err_ratio(y_slow.float().cpu(), y_fast.float().cpu()) < 1.5e-2

@@ -1,0 +1,60 @@
+"""Wan2.1-1.3B MHLA layer (dim 1536, 12 heads, D = 128, 21x30x50 tokens, layout (3,5,10)): the fused inference path
+(one pre-processing launch + the blockmix kernel's 3-D block view) against the module's reference-style path (torch
+pre-processing + block-major rearrange copies), whole-module forward under bf16 autocast.  GPU box only."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import mhla_b200  # noqa: E402
+from mhla_b200.modules import MHLA_Video_Uni  # noqa: E402
+from mhla_b200.modules.wan import _rope_tables  # noqa: E402
+
+
+def rope_freqs(d, n=1024):
+    def rp(dim):
+        fr = torch.outer(torch.arange(n), 1.0 / torch.pow(10000, torch.arange(0, dim, 2).to(torch.float64).div(dim)))
+        return torch.polar(torch.ones_like(fr), fr)
+    return torch.cat([rp(d - 4 * (d // 6)), rp(2 * (d // 6)), rp(2 * (d // 6))], dim=1)
+
+
+def timed(fn, reps=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
+dim, heads, layout, grid = 1536, 12, (3, 5, 10), (21, 30, 50)
+N = grid[0] * grid[1] * grid[2]
+freqs = rope_freqs(dim // heads)
+for B, norm in ((1, False), (2, False), (2, True)):
+    m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=norm).cuda().eval()
+    x = torch.randn(B, N, dim, device="cuda")
+    gs = torch.tensor([list(grid)] * B, dtype=torch.long)
+    sl = torch.tensor([N] * B)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        m.fast_path = True
+        t_fast = timed(lambda: m(x, sl, gs, freqs))
+        y1 = m(x, sl, gs, freqs)
+        m.fast_path = False
+        t_slow = timed(lambda: m(x, sl, gs, freqs))
+        y2 = m(x, sl, gs, freqs)
+        # the operator alone on token-major tensors (3-D block view)
+        q = torch.randn(B, N, heads, dim // heads, device="cuda").bfloat16()
+        W = m.block_attn.conv.weight
+        t_op = timed(lambda: mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False))
+        cos, sin = _rope_tables(grid, freqs, x.device)
+        xq = torch.randn(B, N, dim, device="cuda").bfloat16()
+        t_prep = timed(lambda: mhla_b200.wan_prep(xq, xq, m.norm_q.weight, m.norm_k.weight, cos, sin, dim // heads, want_plain=norm))
+    err = float((y1.float() - y2.float()).norm() / y2.float().norm())
+    print(f"B={B} normalize_out={norm}: module forward fused {t_fast:.0f} us vs reference-style {t_slow:.0f} us "
+          f"({t_slow / t_fast:.2f}x), rel diff {err:.2e}; operator (3-D view, no norm) {t_op:.0f} us, prep kernel {t_prep:.0f} us")
