@@ -81,7 +81,7 @@ typedef struct mhla_tensor5 {
  * where Qn/Kn are q_rope/k_rope when given (variant B) and q/k otherwise, while the normaliser always
  * uses the un-roped q/k (mhla_utils.py:334-338).
  * Envelope: D in {64, 128} (Dk == Dv); 1 <= w <= 256; M >= 1; bf16 or fp16 I/O, fp32 accumulation,
- * TF32 block mixing; mix is fp32 [M, M] row-major with leading dimension mix_ld (elements).
+ * block mixing as a hi+lo 16-bit GEMM (~16 mantissa bits); mix is fp32 [M, M] row-major with leading dimension mix_ld (elements).
  */
 typedef struct mhla_blockmix_desc {
   int32_t B, H, M, w, D;

@@ -609,7 +609,8 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   const uintptr_t al = reinterpret_cast<uintptr_t>(d->xq) | reinterpret_cast<uintptr_t>(d->xk) |
                        reinterpret_cast<uintptr_t>(d->q_rope) | reinterpret_cast<uintptr_t>(d->k_rope) |
                        reinterpret_cast<uintptr_t>(d->q_plain) | reinterpret_cast<uintptr_t>(d->k_plain) |
-                       reinterpret_cast<uintptr_t>(d->cos_table) | reinterpret_cast<uintptr_t>(d->sin_table);
+                       reinterpret_cast<uintptr_t>(d->cos_table) | reinterpret_cast<uintptr_t>(d->sin_table) |
+                       reinterpret_cast<uintptr_t>(d->wq) | reinterpret_cast<uintptr_t>(d->wk);
   if ((al & 15) != 0 || d->ld_in % 8 != 0 || (d->D / 2) % 4 != 0) return MHLA_ERR_ALIGNMENT;
   mhla::WanPrepParams P{};
   P.xq = d->xq; P.xk = d->xk; P.q_rope = d->q_rope; P.k_rope = d->k_rope; P.q_plain = d->q_plain; P.k_plain = d->k_plain;

@@ -81,11 +81,15 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
   if (!act) return;
   const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
   const float rk = p.wk ? rsqrtf(sk / (float)p.C + p.eps_norm) : 1.f;
+  float wqv[8], wkv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { wqv[i] = 1.f; wkv[i] = 1.f; }
+  if (p.wq) load8<2>(p.wq, c0, wqv);      // two 16-byte loads per weight vector (L1-resident after the first rows)
+  if (p.wk) load8<2>(p.wk, c0, wkv);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const float wqv = p.wq ? __ldg(p.wq + c0 + i) : 1.f, wkv = p.wk ? __ldg(p.wk + c0 + i) : 1.f;
-    q[i] = fmaxf(q[i] * rq * wqv, 0.f) + p.eps;
-    k[i] = fmaxf(k[i] * rk * wkv, 0.f) + p.eps;
+    q[i] = fmaxf(q[i] * rq * wqv[i], 0.f) + p.eps;
+    k[i] = fmaxf(k[i] * rk * wkv[i], 0.f) + p.eps;
   }
   const long long o = (long long)row * p.C + c0;
   if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
