@@ -81,3 +81,99 @@ def mhla_sharded(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, mix: torch.T
         a, b = unit_range(G, world, r)
         pieces.append(buf[r * per: r * per + (b - a)])
     return torch.cat(pieces, dim=0)
+
+
+# ------------------------------------------------------------------------------------------------ block-range split
+def _phase_call(q, k, v, mix, normalize, eps, q_rope, k_rope, flags_extra, ws, out=None):
+    """One phase (or phase range) of the general kernel on a caller-owned workspace, through the C ABI's phase flags."""
+    import ctypes as C
+    from . import _capi
+    from .ops import _DT, _t5
+    B, H, M, w, D = q.shape
+    d = _capi.BlockmixDesc()
+    d.B, d.H, d.M, d.w, d.D = B, H, M, w, D
+    d.dtype, d.eps = _DT[q.dtype], float(eps)
+    d.flags = (_capi.FLAG_NORMALIZE if normalize else 0) | _capi.FLAG_UNFUSED | _capi.FLAG_NO_SMALLN | flags_extra
+    o = out if out is not None else torch.empty_like(q)
+    d.q, d.k, d.v, d.out = _t5(q), _t5(k), _t5(v), _t5(o)
+    d.q_rope, d.k_rope = _t5(q_rope), _t5(k_rope)
+    d.mix, d.mix_ld = mix.data_ptr(), mix.stride(0)
+    L = _capi.lib()
+    nbytes = L.mhla_blockmix_workspace_bytes(C.byref(d))
+    lay = (C.c_size_t * 8)()
+    _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
+    if ws is None:
+        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    d.workspace, d.workspace_bytes = ws.data_ptr() + base, nbytes
+    with torch.cuda.device(q.device):
+        _capi.check(L.mhla_fwd_blockmix(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_fwd_blockmix")
+    ncols, wpad = int(lay[5]), int(lay[6])
+    G = B * H
+    views = dict(
+        S=ws[base + lay[0]: base + lay[0] + G * M * ncols * 2].view(torch.int16).view(G, M, ncols),
+        St=ws[base + lay[1]: base + lay[1] + G * M * D * D * 2].view(torch.int16).view(G, M, D * D),
+        den=(ws[base + lay[2]: base + lay[2] + G * M * 2 * wpad * 4].view(torch.float32).view(G, M, 2 * wpad) if wpad else None))
+    return o, ws, views
+
+
+def mhla_block_sharded(q, k, v, mix, *, group=None, normalize: bool = True, eps: float = 1e-6, q_rope=None, k_rope=None):
+    """Block-range split (second axis) for B*H smaller than / not divisible by the number of GPUs - Wan with
+    guidance off: 12 heads on 8 GPUs.  Every rank holds ALL (b,h) units but only its contiguous range of blocks:
+    q, k, v (and the roped copies) are [B, H, Mloc, w, D] with Mloc = unit_range(M, world, rank); ``mix`` is the full [M, M]
+    matrix.  Three phases of the same kernel with ONE exchange step between them:
+      1. block summaries S_j (+ ksum / n_loc) of the local blocks                       (phase 1 on the local blocks)
+      2. all-gather of the summaries - M * (D^2 + 2 wpad) 16-bit values per unit - and the block mixing of the full set
+         (phase 2; small and identical on every rank: replicated rather than exchanged a second time)
+      3. readout of the local blocks against their rows of S~ / den                      (phase 3 on the local blocks)
+    Returns the local [B, H, Mloc, w, D] slice of the output: no gather is needed when the consumer is token-sharded."""
+    from . import _capi
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    B, H, Mloc, w, D = q.shape
+    M = mix.shape[0]
+    lo, hi = unit_range(M, world, rank)
+    if hi - lo != Mloc:
+        raise ValueError("local block slices must follow unit_range(M, world, rank)")
+    mixf = mix.detach().reshape(M, M).float().contiguous()
+    dummy = mixf[:Mloc, :Mloc].contiguous()
+    # 1. local summaries
+    _, ws_loc, v_loc = _phase_call(q, k, v, dummy, normalize, eps, q_rope, k_rope, _capi.FLAG_STOP_AFTER_P1, None)
+    # 2. exchange + mixing of the full set
+    per = -(-M // world)
+    G, ncols = B * H, v_loc["S"].shape[-1]
+    send = v_loc["S"].new_zeros((G, per, ncols))
+    send[:, :Mloc] = v_loc["S"]
+    recv = send.new_empty((world, G, per, ncols))
+    if world > 1:   # (NCCL has no int16: the 16-bit summaries travel as raw bytes)
+        dist.all_gather_into_tensor(recv.view(torch.uint8), send.view(torch.uint8), group=group)
+    else:
+        recv[0] = send
+    qf = q.new_empty((B, H, M, w, D))          # shape carrier for the full descriptor (phase 2 touches no q/k/v)
+    ws_full = None
+    # (allocate the full workspace through a dry layout query: phase 2 only)
+    import ctypes as C
+    from .ops import _DT
+    d = _capi.BlockmixDesc()
+    d.B, d.H, d.M, d.w, d.D = B, H, M, w, D
+    d.dtype, d.flags, d.eps = _DT[q.dtype], (_capi.FLAG_NORMALIZE if normalize else 0) | _capi.FLAG_UNFUSED | _capi.FLAG_NO_SMALLN, float(eps)
+    if q_rope is not None:
+        d.q_rope.ptr = d.k_rope.ptr = 1
+    L = _capi.lib()
+    nbytes = L.mhla_blockmix_workspace_bytes(C.byref(d))
+    lay = (C.c_size_t * 8)()
+    _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
+    ws_full = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    base = (ws_full.data_ptr() + 1023) // 1024 * 1024 - ws_full.data_ptr()
+    S_full = ws_full[base + lay[0]: base + lay[0] + G * M * ncols * 2].view(torch.int16).view(G, M, ncols)
+    for r in range(world):
+        a, b = unit_range(M, world, r)
+        S_full[:, a:b] = recv[r, :, : b - a]
+    qr_f = qf if q_rope is not None else None
+    _, _, v_full = _phase_call(qf, qf, qf, mixf, normalize, eps, qr_f, qr_f, _capi.FLAG_ONLY_P2, ws_full)
+    # 3. readout of the local blocks
+    v_loc["St"].copy_(v_full["St"][:, lo:hi])
+    if normalize:
+        v_loc["den"].copy_(v_full["den"][:, lo:hi])
+    out, _, _ = _phase_call(q, k, v, dummy, normalize, eps, q_rope, k_rope, _capi.FLAG_ONLY_P3, ws_loc)
+    return out

@@ -68,3 +68,49 @@ def test_sharded_nccl_bitwise_equals_single_gpu(world, shape, normalize):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     _run(world, shape, normalize)
+
+
+def _worker_blocks(rank, world, port, shape, normalize, rope, q_out):
+    import torch.distributed as dist
+    import mhla_b200
+    from mhla_b200.sharded import mhla_block_sharded, unit_range
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        B, H, M, w, D = shape
+        g = torch.Generator().manual_seed(0)
+        mk = lambda relu: ((torch.relu(torch.randn(B, H, M, w, D, generator=g)) + 1e-6) if relu  # noqa: E731
+                           else torch.randn(B, H, M, w, D, generator=g)).bfloat16().to(dev)
+        q, k, v = mk(True), mk(True), mk(False)
+        qr, kr = (mk(False), mk(False)) if rope else (None, None)
+        W = (torch.rand(M, M, generator=g) / M).to(dev)
+        full = mhla_b200.mhla(q, k, v, W, q_rope=qr, k_rope=kr, normalize=normalize, three_launch=True)
+        lo, hi = unit_range(M, world, rank)
+        sl = lambda t: None if t is None else t[:, :, lo:hi].contiguous()  # noqa: E731
+        out = mhla_block_sharded(sl(q), sl(k), sl(v), W, normalize=normalize, q_rope=sl(qr), k_rope=sl(kr))
+        torch.cuda.synchronize()
+        q_out.put((rank, bool(torch.equal(out, full[:, :, lo:hi])), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+@pytest.mark.parametrize("shape,normalize,rope", [((1, 3, 30, 210, 128), False, True), ((1, 2, 19, 64, 64), True, False)])
+def test_block_range_split_nccl_bitwise(world, shape, normalize, rope):
+    """Block-range split (one all-gather of the block summaries): each rank's slice of the output is BITWISE the
+    single-GPU result - Wan-shaped blocks (210 tokens, D = 128, roped numerator) and an uneven split with the normaliser."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    ctx = mp.get_context("spawn")
+    q_out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_blocks, args=(r, world, port, shape, normalize, rope, q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    results = sorted(q_out.get(timeout=10) for _ in range(world))
+    assert all(ok for _, ok, _ in results), results
