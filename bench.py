@@ -268,7 +268,6 @@ def main():
     ap.add_argument("--no-normalize", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
-    ap.add_argument("--graph", action="store_true", help="replay CUDA graphs also below 4 ranks")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
     args = ap.parse_args()
@@ -321,19 +320,24 @@ def main():
         if gather:
             dist.all_gather_into_tensor(gathered, out)
 
-    # A step = one launch of the operator on this rank's units.  The launches are replayed from CUDA graphs (one per
-    # rotating input set, captured after warm-up) so that the Python / ctypes enqueue cost (~25 us per call) does not
-    # sit on the timed path when the sharded kernel itself only takes 30-40 us (N = 8); `--no-graph` times eager calls.
-    graphs = []
+    def launch(i, gather=False):
+        q, k, v, out = sets[i % nsets]
+        mhla_sharded(q, k, v, W, inputs="local", total_units=UNITS, gather=False, normalize=normalize, out=out, **path_kw)
+        if gather:
+            dist.all_gather_into_tensor(gathered, out)
+
+    # A step = one launch of the operator on this rank's units.  The K timed steps are captured into ONE CUDA graph (after
+    # warm-up) and replayed: the launches keep their programmatic-dependent-launch edges inside the graph, so consecutive
+    # steps overlap prologue and tail exactly like eager back-to-back launches, but the Python / ctypes enqueue cost
+    # (~25 us per call) is off the timed path - it matters from 4 ranks on, where the per-rank kernel is that short.
+    # `--no-graph` times eager calls.
+    graph = [None]
     it = [0]
 
     def step(gather=False):
         i = it[0]
         it[0] += 1
-        if graphs and not gather:
-            graphs[i % nsets].replay()
-        else:
-            launch(i, gather)
+        launch(i, gather)
 
     # quick self-check of one (b,h) unit against the oracle before timing anything
     step()
@@ -343,21 +347,19 @@ def main():
     if not err < 5e-3:
         raise SystemExit(f"bench self-check failed: err_ratio {err}")
     it[0] = 0
-    # (graph replays pay ~1.5 us per step for the lost PDL overlap between consecutive launches: only worth it once the
-    #  per-rank kernel is as short as the ~25 us Python enqueue, i.e. from 4 ranks on)
-    if not args.no_graph and (world >= 4 or args.graph):
+    if not args.no_graph:
         try:
             for i in range(nsets):
                 launch(i)                                  # warm every set's descriptors / workspace
             torch.cuda.synchronize()
-            for i in range(nsets):
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                for i in range(args.steps):
                     launch(i)
-                graphs.append(gr)
+            graph[0] = gr
         except Exception as e:   # noqa: BLE001
             print(f"CUDA graph capture failed ({e!r}); timing eager launches", file=sys.stderr)
-            graphs.clear()
+            graph[0] = None
 
     def timed_loop(gather):
         for _ in range(warm):
@@ -368,8 +370,11 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(args.steps):
-            step(gather)
+        if graph[0] is not None and not gather:
+            graph[0].replay()                              # = exactly args.steps launches
+        else:
+            for _ in range(args.steps):
+                step(gather)
         e1.record()
         torch.cuda.synchronize()
         if dist is not None:
@@ -428,7 +433,8 @@ def main():
             "workload": f"blockmix A (mhla_dit core): B={B} H={H} N={N} D={D} w={WBLK} M={M} normalize={int(normalize)} (whole job)",
             "parallelism": (f"{UNITS} (b,h) units sharded over {world} rank(s), {nloc} per GPU, no data-path collective"
                             + ("; with_gather adds one NCCL all_gather_into_tensor of the outputs behind the kernel" if ms_gather else "")),
-            "launch": "CUDA-graph replay of one operator launch per step" if graphs else "eager launch per step",
+            "launch": (f"one CUDA graph of the {args.steps} timed launches (PDL edges kept), replayed once" if graph[0] is not None
+                       else "eager launch per step"),
             "l2": (f"{nsets} rotating input/output set(s) of {set_bytes / 1e6:.0f} MB per rank: working set "
                    f"{nsets * set_bytes / 1e6:.0f} MB > 126 MB L2 (no explicit flush)"),
         },

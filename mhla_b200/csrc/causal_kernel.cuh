@@ -501,11 +501,14 @@ template <int DK, int DV>
 inline int causal_launch(CausalParams& P, const CausalPlan& pl, int unfused, int num_sms, cudaStream_t stream,
                          int* launches) {
   auto kern = causal_kernel<DK, DV>;
-  static bool attr = false;
-  if (!attr) {
+  // the dynamic shared-memory opt-in is a per-device function attribute: track it per device ordinal
+  static bool attr[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return MHLA_ERR_CUDA;
+  if (!attr[dev]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemAlloc) != cudaSuccess)
       return MHLA_ERR_CUDA;
-    attr = true;
+    attr[dev] = true;
   }
   constexpr int NVH = DV > 128 ? DV / 128 : 1;
   const long long n1 = pl.ns, n2 = (long long)pl.n2_rows * pl.n2_cols, n3 = (long long)pl.ns * NVH;

@@ -619,9 +619,17 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   P.eps_norm = d->eps_norm; P.eps = d->eps;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   const int threads = ((d->C / 8) + 31) / 32 * 32;
-  if (d->in_dtype == 0) mhla::wan_prep_kernel<0><<<d->rows, threads, 0, stream>>>(P);
-  else if (d->in_dtype == 1) mhla::wan_prep_kernel<1><<<d->rows, threads, 0, stream>>>(P);
-  else mhla::wan_prep_kernel<2><<<d->rows, threads, 0, stream>>>(P);
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  int per_sm = 2048 / threads;                     // resident CTAs per SM by threads
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  const long long want = (long long)dst->sms * per_sm;
+  const int grid = (int)(d->rows < want ? d->rows : want);
+  if (d->in_dtype == 0) mhla::wan_prep_kernel<0><<<grid, threads, 0, stream>>>(P);
+  else if (d->in_dtype == 1) mhla::wan_prep_kernel<1><<<grid, threads, 0, stream>>>(P);
+  else mhla::wan_prep_kernel<2><<<grid, threads, 0, stream>>>(P);
   if (!cuda_ok(cudaGetLastError(), "wan_prep_kernel")) return MHLA_ERR_CUDA;
   g_last_launches = 1;
   return MHLA_OK;

@@ -58,56 +58,72 @@ __device__ __forceinline__ void store8(void* base, long long idx, const float (&
 
 template <int IN>
 __global__ void wan_prep_kernel(const WanPrepParams p) {
-  __shared__ float red[2][32];
-  const int row = blockIdx.x;
+  // Persistent over token rows (grid = a few CTAs per SM): the loads of the NEXT row are issued before the current row is
+  // reduced, normalised and stored, so every thread keeps two rows of reads in flight (one CTA per token left the
+  // memory system at 2.6 TB/s: each row's load -> block reduction -> store chain was fully exposed).
+  __shared__ float red[2][2][32];
   const int tid = threadIdx.x;
   const int c0 = tid * 8;
   const bool act = c0 < p.C;
-  float q[8], k[8];
-  float sq = 0.f, sk = 0.f;
-  if (act) {
-    load8<IN>(p.xq, (long long)row * p.ld_in + c0, q);
-    load8<IN>(p.xk, (long long)row * p.ld_in + c0, k);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { sq = fmaf(q[i], q[i], sq); sk = fmaf(k[i], k[i], sk); }
-  }
-  // block-wide sums of squares (the norm runs over the FULL channel dim, across heads: wan/model.py:181-196)
-  for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
-  if ((tid & 31) == 0) { red[0][tid >> 5] = sq; red[1][tid >> 5] = sk; }
-  __syncthreads();
   const int nw = (blockDim.x + 31) >> 5;
-  sq = 0.f; sk = 0.f;
-  for (int i = 0; i < nw; ++i) { sq += red[0][i]; sk += red[1][i]; }
-  if (!act) return;
-  const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
-  const float rk = p.wk ? rsqrtf(sk / (float)p.C + p.eps_norm) : 1.f;
   float wqv[8], wkv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { wqv[i] = 1.f; wkv[i] = 1.f; }
-  if (p.wq) load8<2>(p.wq, c0, wqv);      // two 16-byte loads per weight vector (L1-resident after the first rows)
-  if (p.wk) load8<2>(p.wk, c0, wkv);
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    q[i] = fmaxf(q[i] * rq * wqv[i], 0.f) + p.eps;
-    k[i] = fmaxf(k[i] * rk * wkv[i], 0.f) + p.eps;
+  if (act && p.wq) load8<2>(p.wq, c0, wqv);
+  if (act && p.wk) load8<2>(p.wk, c0, wkv);
+  float qn[8], kn[8];
+  int row = blockIdx.x;
+  if (act && row < p.rows) {
+    load8<IN>(p.xq, (long long)row * p.ld_in + c0, qn);
+    load8<IN>(p.xk, (long long)row * p.ld_in + c0, kn);
   }
-  const long long o = (long long)row * p.C + c0;
-  if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
-  if (p.cos_t) {
-    // interleaved-pair rotation (view_as_complex, mhla_utils.py:144-151): pair i of a head takes angle [token, i]
-    const int tok = row % p.N, d0 = c0 % p.D;                  // 8 channels never straddle a head (D % 8 == 0)
-    const float4 cs = __ldg(reinterpret_cast<const float4*>(p.cos_t + (long long)tok * (p.D / 2) + d0 / 2));
-    const float4 sn = __ldg(reinterpret_cast<const float4*>(p.sin_t + (long long)tok * (p.D / 2) + d0 / 2));
-    const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
+  for (int it = 0; row < p.rows; row += gridDim.x, ++it) {
+    float q[8], k[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float a = q[2 * i], b = q[2 * i + 1], a2 = k[2 * i], b2 = k[2 * i + 1];
-      q[2 * i] = a * c4[i] - b * s4[i]; q[2 * i + 1] = a * s4[i] + b * c4[i];
-      k[2 * i] = a2 * c4[i] - b2 * s4[i]; k[2 * i + 1] = a2 * s4[i] + b2 * c4[i];
+    for (int i = 0; i < 8; ++i) { q[i] = qn[i]; k[i] = kn[i]; }
+    const int nrow = row + gridDim.x;
+    if (act && nrow < p.rows) {
+      load8<IN>(p.xq, (long long)nrow * p.ld_in + c0, qn);
+      load8<IN>(p.xk, (long long)nrow * p.ld_in + c0, kn);
     }
+    float sq = 0.f, sk = 0.f;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sq = fmaf(q[i], q[i], sq); sk = fmaf(k[i], k[i], sk); }
+    }
+    // block-wide sums of squares (the norm runs over the FULL channel dim, across heads: wan/model.py:181-196)
+    for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
+    float (*rd)[32] = red[it & 1];                 // alternate buffers: one barrier per row
+    if ((tid & 31) == 0) { rd[0][tid >> 5] = sq; rd[1][tid >> 5] = sk; }
+    __syncthreads();
+    if (!act) continue;
+    sq = 0.f; sk = 0.f;
+    for (int i = 0; i < nw; ++i) { sq += rd[0][i]; sk += rd[1][i]; }
+    const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
+    const float rk = p.wk ? rsqrtf(sk / (float)p.C + p.eps_norm) : 1.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      q[i] = fmaxf(q[i] * rq * wqv[i], 0.f) + p.eps;
+      k[i] = fmaxf(k[i] * rk * wkv[i], 0.f) + p.eps;
+    }
+    const long long o = (long long)row * p.C + c0;
+    if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
+    if (p.cos_t) {
+      // interleaved-pair rotation (view_as_complex, mhla_utils.py:144-151): pair i of a head takes angle [token, i]
+      const int tok = row % p.N, d0 = c0 % p.D;                  // 8 channels never straddle a head (D % 8 == 0)
+      const float4 cs = __ldg(reinterpret_cast<const float4*>(p.cos_t + (long long)tok * (p.D / 2) + d0 / 2));
+      const float4 sn = __ldg(reinterpret_cast<const float4*>(p.sin_t + (long long)tok * (p.D / 2) + d0 / 2));
+      const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = q[2 * i], b = q[2 * i + 1], a2 = k[2 * i], b2 = k[2 * i + 1];
+        q[2 * i] = a * c4[i] - b * s4[i]; q[2 * i + 1] = a * s4[i] + b * c4[i];
+        k[2 * i] = a2 * c4[i] - b2 * s4[i]; k[2 * i + 1] = a2 * s4[i] + b2 * c4[i];
+      }
+    }
+    store8(p.q_rope, o, q, p.out_fp16);
+    store8(p.k_rope, o, k, p.out_fp16);
   }
-  store8(p.q_rope, o, q, p.out_fp16);
-  store8(p.k_rope, o, k, p.out_fp16);
 }
 
 }  // namespace mhla

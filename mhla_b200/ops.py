@@ -362,9 +362,15 @@ def mhla_host(q, k, v, mix, *, out: Optional[torch.Tensor] = None, device=None, 
     """Block-mixed forward for HOST tensors ([B, H, M, w, D], ideally pinned): the (b,h) units are independent, so the
     batch is cut into `chunks` contiguous ranges of units and the host->device copies of range c+1, the kernel of range
     c and the device->host copy of range c-1 run concurrently on three streams (PCIe is full duplex; the kernel time
-    disappears behind the copies).  Returns a host tensor (`out`, pinned if given so, else freshly pinned)."""
+    disappears behind the copies).  Returns a host tensor (`out`, pinned if given so, else freshly pinned).
+
+    The device->host copies are ASYNCHRONOUS: the caller's current stream is made to wait for them, so any later work on
+    that stream is ordered, but the HOST must synchronise (``torch.cuda.current_stream().synchronize()``) before reading
+    `out` from Python.  `out` must be contiguous (it is written through a reshaped view)."""
     if q.is_cuda:
         raise ValueError("mhla_host takes host tensors; use mhla() for device tensors")
+    if out is not None and not out.is_contiguous():
+        raise ValueError("mhla_host: out must be contiguous")
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     B, H, M, w, D = q.shape
     if out is None:
