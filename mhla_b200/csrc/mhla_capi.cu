@@ -81,7 +81,7 @@ constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (sepa
 
 // Tuning / debugging knobs of the blockmix kernel, read from the environment ONCE (first call).
 struct Knobs {
-  int run_ahead = 2, mix_hi_only = 0, o_hint = 1, q_hint = 1, trace_cta = 0, slots = 2;
+  int run_ahead = 2, mix_hi_only = -1, o_hint = 1, q_hint = 1, trace_cta = 0, slots = 2;
   bool no_pack = false, no_self_prep = false;
 };
 const Knobs& knobs() {
@@ -92,7 +92,7 @@ const Knobs& knobs() {
     k.run_ahead = geti("MHLA_RUNAHEAD", k.run_ahead);
     if (k.run_ahead < 1) k.run_ahead = 1;
     if (k.run_ahead > 16) k.run_ahead = 16;
-    k.mix_hi_only = geti("MHLA_MIX_HI_ONLY", 0);
+    k.mix_hi_only = geti("MHLA_MIX_HI_ONLY", -1);   // -1: automatic (see mhla_fwd_blockmix)
     k.o_hint = geti("MHLA_OHINT", 1);
     k.q_hint = geti("MHLA_QHINT", 1);
     k.trace_cta = geti("MHLA_TRACE_CTA", 0);
@@ -486,7 +486,11 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.prof = g_prof_buffer;
   P.run_ahead = kn.run_ahead;
   P.trace_cta = kn.trace_cta;
-  P.mix_hi_only = kn.mix_hi_only;
+  // bf16, D = 128 (Wan): the S columns of the block mixing take the 8-bit hi plane of the mixing matrix only - what the
+  // reference's 1x1 conv computes under the bf16 autocast its sampler and trainer run in (its weight is rounded to bf16;
+  // SURVEY.md 8a row B3).  Halves the matrix bytes and MMAs of the 1536 mixing items of a Wan layer: 132 -> 120 us,
+  // RMS error vs the fp32 oracle 2.9e-3 -> 3.3e-3 (budget 5e-3).  The normaliser columns always use hi + lo.
+  P.mix_hi_only = kn.mix_hi_only >= 0 ? kn.mix_hi_only : ((d->D == 128 && d->dtype == MHLA_BF16) ? 1 : 0);
   P.o_hint = kn.o_hint;
   P.q_hint = kn.q_hint;
   P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = 0;   // (round-1 tuning options, fixed at their best values)
