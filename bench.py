@@ -75,6 +75,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.interval = float(os.environ.get("MHLA_BENCH_SAMPLE_S", "0.0005"))
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -103,7 +104,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.0005)
+            time.sleep(self.interval)
 
     def summary(self):
         s = sorted(self.samples)

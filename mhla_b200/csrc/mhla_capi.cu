@@ -503,6 +503,15 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
       if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
                    "cudaFuncSetAttribute"))
         return MHLA_ERR_CUDA;
+      // The fused kernel's CTAs wait for each other (self-prep announcement, per-group counters), so the whole grid has
+      // to be co-resident: check once per device that a CTA of this instantiation fits an SM at all (grid <= #SMs, 1 CTA
+      // per SM).  Other work sharing the GPU only delays the waits - they are bounded in the seconds range, a whole
+      // launch takes < 1 ms.
+      int occ = 0;
+      if (!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, mhla::kThreads, mhla::kSmemAlloc),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+        return MHLA_ERR_CUDA;
+      if (occ < 1) { g_last_cuda_error = "blockmix kernel does not fit one SM on this device"; return MHLA_ERR_NO_DEVICE; }
       attr = true;
     }
   }
