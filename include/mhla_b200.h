@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MHLA_B200_ABI_VERSION 3
+#define MHLA_B200_ABI_VERSION 4
 
 typedef enum mhla_status {
   MHLA_OK = 0,
@@ -110,12 +110,21 @@ typedef struct mhla_blockmix_desc {
    * inverse disappear.  Envelope: p2*p3 <= 128 and ceil(p1 / floor(128 / (p2*p3))) <= 2 sub-tiles. */
   int32_t grid[3];
   int32_t layout[3];
+  /* Further fused post-ops of the readout epilogue (ABI v4), applied in fp32 before the single
+   * rounding, after the normaliser and the optional per-head RMS normalisation:
+   *     out = o * silu(out_gate) + out_add
+   * - the SiLU output gate and the "+ lepe" term of the Wan classes (mhla_videogen/diffusion/model/wan/mhla_utils.py
+   * :363-365, wan/model.py:995-1001) and the "+ lepe" of MHLA4DiT (mhla_dit/mhla/mhla.py:271-273).  Both are 16-bit
+   * tensors of the I/O dtype shaped like `out`, with their own strides (block-major or, with the 3-D block view,
+   * token-major: e.g. plain views of the gate projection g(x) and of the depthwise-conv output); ptr == NULL: off. */
+  mhla_tensor5 out_gate;
+  mhla_tensor5 out_add;
 } mhla_blockmix_desc;
 
 size_t mhla_blockmix_workspace_bytes(const mhla_blockmix_desc* desc);
 /* 1 when mhla_fwd_blockmix(desc) uses the workspace; 0 for shapes that take the short-sequence kernel (M*w <= 256 tokens
- * per (b,h) unit, D = 64, M <= 64, no rope / fused output norm): workspace may then be NULL.  Pointers in desc are ignored
- * except that q_rope / k_rope / out_rms_weight must be NULL or non-NULL as in the later call. */
+ * per (b,h) unit, D = 64, M <= 64, no rope / fused output norm / gate): workspace may then be NULL.  Pointers in desc are
+ * ignored except that q_rope / k_rope / out_rms_weight / out_gate must be NULL or non-NULL as in the later call. */
 int mhla_blockmix_needs_workspace(const mhla_blockmix_desc* desc);
 /* White-box view of the workspace for tests: out[0..7] = byte offsets of S, S~, den, padded mix, counters,
  * then ncols (floats per S row: D*D summaries followed by wpad n_loc entries), wpad, padded mix pitch. */
@@ -176,6 +185,36 @@ typedef struct mhla_wan_prep_desc {
 
 int mhla_wan_prep(const mhla_wan_prep_desc* desc, void* stream);
 int mhla_fwd_causal(const mhla_causal_desc* desc, void* stream);
+
+/*
+ * Backward (trainers mhla_dit/train.py:298-310, mhla_videogen/train_wan.py:717).  The gradient
+ * CONTRACTIONS of variants A / B are calls of mhla_fwd_blockmix itself with permuted operands,
+ *   dQ = blockmix(q = dO~, k = V,   v = K,   mix)          dV = blockmix(q = K, k = Q, v = dO~, mix^T)
+ *   dK = blockmix(q = V,   k = dO~, v = Q,   mix^T)        (no normaliser flag; dO~ = dO / den, or dO itself)
+ * and d mix contracts the block summaries those launches leave in their workspaces (S of the dK launch against S of the
+ * dQ launch).  Variant C likewise through mhla_fwd_causal on time-reversed tensors (mhla_b200/autograd.py).  With the
+ * normaliser (mhla.py:265-268) two streaming passes over contiguous [rows, D] token rows remain:
+ *   mhla_bwd_prep:  dnum[r,:] = dout[r,:] / den[r]   and   dden[r] = -(dout[r,:] . out[r,:]) / den[r]
+ *   mhla_bwd_post:  dq[r,:] = dqn[r,:] + dnl[r] * ksum[r / w, :]   and   dk[r,:] = dkn[r,:] + dksum[r / w, :]
+ * (den: the forward's normaliser; dnl = mix^T dden; ksum = sum_t k[.,t,:]; dksum = sum_t dnl[.,t] q[.,t,:]).
+ * dqn / dkn may both be NULL (roped numerator: the un-roped q, k only feed the normaliser).  D in {64, 128} for prep.
+ */
+typedef struct mhla_bwd_prep_desc {
+  int64_t rows; int32_t D; int32_t dtype;
+  const void* dout; const void* out;  /* [rows, D] 16-bit */
+  const float* den;                   /* [rows] */
+  void* dnum;                         /* [rows, D] 16-bit, written */
+  float* dden;                        /* [rows], written */
+} mhla_bwd_prep_desc;
+typedef struct mhla_bwd_post_desc {
+  int64_t rows; int32_t w, D, dtype;
+  const void* dqn; const void* dkn;   /* [rows, D] 16-bit or NULL */
+  const float* dnl;                   /* [rows] */
+  const float* ksum; const float* dksum; /* [rows / w, D] fp32 */
+  void* dq; void* dk;                 /* [rows, D] 16-bit, written (may alias dqn / dkn) */
+} mhla_bwd_post_desc;
+int mhla_bwd_prep(const mhla_bwd_prep_desc* desc, void* stream);
+int mhla_bwd_post(const mhla_bwd_post_desc* desc, void* stream);
 
 /* Misc. */
 int mhla_abi_version(void);

@@ -22,7 +22,7 @@ FLAG_NO_SMALLN = 1 << 15
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
-    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal", "mhla_wan_prep",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal", "mhla_wan_prep", "mhla_bwd_prep", "mhla_bwd_post",
 ]
 
 
@@ -39,6 +39,7 @@ class BlockmixDesc(C.Structure):
         ("mix", C.c_void_p), ("mix_ld", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
         ("out_rms_weight", C.c_void_p), ("out_rms_eps", C.c_float),
         ("grid", C.c_int32 * 3), ("layout", C.c_int32 * 3),
+        ("out_gate", Tensor5), ("out_add", Tensor5),
     ]
 
 
@@ -65,6 +66,17 @@ class WanPrepDesc(C.Structure):
         ("wq", C.c_void_p), ("wk", C.c_void_p), ("cos_table", C.c_void_p), ("sin_table", C.c_void_p),
         ("eps_norm", C.c_float), ("eps", C.c_float),
     ]
+
+
+class BwdPrepDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("D", C.c_int32), ("dtype", C.c_int32), ("dout", C.c_void_p), ("out", C.c_void_p),
+                ("den", C.c_void_p), ("dnum", C.c_void_p), ("dden", C.c_void_p)]
+
+
+class BwdPostDesc(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("w", C.c_int32), ("D", C.c_int32), ("dtype", C.c_int32), ("dqn", C.c_void_p),
+                ("dkn", C.c_void_p), ("dnl", C.c_void_p), ("ksum", C.c_void_p), ("dksum", C.c_void_p),
+                ("dq", C.c_void_p), ("dk", C.c_void_p)]
 
 
 class MhlaError(RuntimeError):
@@ -106,7 +118,12 @@ def lib() -> C.CDLL:
             L.mhla_wan_prep.argtypes = [C.POINTER(WanPrepDesc), C.c_void_p]
         L.mhla_fwd_causal.restype = C.c_int
         L.mhla_fwd_causal.argtypes = [C.POINTER(CausalDesc), C.c_void_p]
-        if L.mhla_abi_version() != 3:
+        if hasattr(L, "mhla_bwd_prep"):
+            L.mhla_bwd_prep.restype = C.c_int
+            L.mhla_bwd_prep.argtypes = [C.POINTER(BwdPrepDesc), C.c_void_p]
+            L.mhla_bwd_post.restype = C.c_int
+            L.mhla_bwd_post.argtypes = [C.POINTER(BwdPostDesc), C.c_void_p]
+        if L.mhla_abi_version() != 4:
             raise ImportError("libmhla_b200.so ABI version mismatch; rebuild with `python -m mhla_b200.build --force`")
         _lib = L
     return _lib

@@ -99,6 +99,13 @@ struct alignas(64) BlockmixParams {
   const void* g3_zero;                      // >= 2 KB of zeros (workspace): fills a tile up to a multiple of 16 token rows
   int g3_F, g3_hb, g3_wb, g3_p1, g3_p2, g3_p3, g3_aper, g3_tail;
   int g3_rows[2], g3_kpad[2];               // token rows of sub-tile s, and rounded up to the MMA k-step (16)
+  // ---- fused post-ops of the readout epilogue (blockmix_kernel<D, G3D, true>):
+  //   out = (o [/ den] [* rms * rms_w]) * silu(gate) + add       (mhla_utils.py:360-366: g_norm, SiLU gate, + lepe)
+  // gate / add are 16-bit tensors laid out like `out` with their own element strides (3-D view: token stride in *_sw,
+  // *_sm unused); NULL = that op is off.  Each epilogue thread owns one token row and reads its 128-byte pieces directly.
+  const uint16_t* post_gate; const uint16_t* post_add;
+  long long pg_sb, pg_sh, pg_sm, pg_sw, pa_sb, pa_sh, pa_sm, pa_sw;
+  int g3_H, g3_W;                           // token grid (3-D view): rows of a frame, tokens of a row
 };
 
 // 1-D bulk copy global -> shared, completion counted on an mbarrier (bytes multiple of 16, 16-byte aligned addresses)
@@ -249,7 +256,7 @@ __device__ __forceinline__ int p3_stages(const BlockmixParams& p) {
   else return 1 + p.nsub;
 }
 
-template <int D, bool G3D = false>
+template <int D, bool G3D = false, bool POST = false>
 __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_constant__ BlockmixParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -917,6 +924,45 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         }
       }
     };
+    // same with the fused post-ops (POST instantiations only): optional per-column weight, SiLU gate and additive term
+    // read from the token row's own 128-byte pieces of the gate / add tensors; 32 columns at a time (register budget)
+    auto load_pack64_post = [&](uint32_t taddr, float scale, const float* wcol, const uint16_t* grow, const uint16_t* arow,
+                                uint32_t* pk) {
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t gw[16], aw[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 g4 = make_uint4(0u, 0u, 0u, 0u), a4 = make_uint4(0u, 0u, 0u, 0u);
+          if (grow != nullptr) g4 = __ldg(reinterpret_cast<const uint4*>(grow + hh * 32) + i);
+          if (arow != nullptr) a4 = __ldg(reinterpret_cast<const uint4*>(arow + hh * 32) + i);
+          gw[4 * i] = g4.x; gw[4 * i + 1] = g4.y; gw[4 * i + 2] = g4.z; gw[4 * i + 3] = g4.w;
+          aw[4 * i] = a4.x; aw[4 * i + 1] = a4.y; aw[4 * i + 2] = a4.z; aw[4 * i + 3] = a4.w;
+        }
+        tmem_ld_x32(taddr + hh * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          float x0 = __uint_as_float(v[2 * e]) * scale, x1 = __uint_as_float(v[2 * e + 1]) * scale;
+          if (wcol != nullptr) { x0 *= __ldg(wcol + hh * 32 + 2 * e); x1 *= __ldg(wcol + hh * 32 + 2 * e + 1); }
+          float2 g2, a2;
+          if (p.is_fp16) {
+            g2 = __half22float2(*reinterpret_cast<const __half2*>(&gw[e]));
+            a2 = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+          } else {
+            g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
+            a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+          }
+          if (grow != nullptr) {   // SiLU(g) = g / (1 + exp(-g))
+            x0 *= __fdividef(g2.x, 1.0f + __expf(-g2.x));
+            x1 *= __fdividef(g2.y, 1.0f + __expf(-g2.y));
+          }
+          x0 += a2.x; x1 += a2.y;   // (zeros when the additive term is off)
+          if (p.is_fp16) { __half2 h0 = __floats2half2_rn(x0, x1); pk[hh * 16 + e] = *reinterpret_cast<uint32_t*>(&h0); }
+          else pk[hh * 16 + e] = pack_bf16x2(x0, x1);
+        }
+      }
+    };
     // x = hi + lo with hi, lo in the 16-bit I/O type
     auto split16 = [&](float x, uint16_t& hi, uint16_t& lo) {
       if (p.is_fp16) {
@@ -1134,9 +1180,33 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
             rden *= rsqrtf(ss * (1.0f / D) + p.rms_eps);
           }
+          // fused post-ops: this thread's token row inside the gate / add tensors (rows beyond the block are never stored)
+          const uint16_t* grow = nullptr;
+          const uint16_t* arow = nullptr;
+          if constexpr (POST) {
+            bool rvalid;
+            long long tsel;   // block-major: token inside the block; 3-D view: token inside the sample
+            if constexpr (!G3D) {
+              const int t = sub * p.TW + et;
+              rvalid = et < p.TW && t < p.w;
+              tsel = t;
+            } else {
+              rvalid = et < p.g3_rows[sub];
+              const int pp = p.g3_p2 * p.g3_p3, a = et / pp, rem = et - a * pp, y = rem / p.g3_p3, x = rem - y * p.g3_p3;
+              const int wbi = ib % p.g3_wb, jj = ib / p.g3_wb, hbi = jj % p.g3_hb, fbi = jj / p.g3_hb;
+              tsel = ((long long)(fbi * p.g3_p1 + sub * p.g3_aper + a) * p.g3_H + hbi * p.g3_p2 + y) * p.g3_W + wbi * p.g3_p3 + x;
+            }
+            if (rvalid && p.post_gate != nullptr)
+              grow = p.post_gate + b * p.pg_sb + h * p.pg_sh + (G3D ? 0 : ib * p.pg_sm) + tsel * p.pg_sw;
+            if (rvalid && p.post_add != nullptr)
+              arow = p.post_add + b * p.pa_sb + h * p.pa_sh + (G3D ? 0 : ib * p.pa_sm) + tsel * p.pa_sw;
+          }
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
-            if (p.rms_w != nullptr) load_pack64_w(acc + sub * 128 + c * 64, rden, p.rms_w + c * 64, pk);
+            if constexpr (POST) {
+              load_pack64_post(acc + sub * 128 + c * 64, rden, p.rms_w != nullptr ? p.rms_w + c * 64 : nullptr,
+                               grow != nullptr ? grow + c * 64 : nullptr, arow != nullptr ? arow + c * 64 : nullptr, pk);
+            } else if (p.rms_w != nullptr) load_pack64_w(acc + sub * 128 + c * 64, rden, p.rms_w + c * 64, pk);
             else load_pack64(acc + sub * 128 + c * 64, rden, pk);
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);

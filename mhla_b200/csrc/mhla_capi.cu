@@ -16,6 +16,7 @@
 #include "causal_kernel.cuh"
 #include "smalln_kernel.cuh"
 #include "wan_prep_kernel.cuh"
+#include "bwd_aux_kernel.cuh"
 
 namespace {
 
@@ -287,6 +288,11 @@ int build_blockmix_params(const mhla_blockmix_desc* d, const BlockmixPlan& pl, m
   P->counters = reinterpret_cast<uint32_t*>(ws + pl.off_cnt);
   P->wscale = reinterpret_cast<const float*>(P->counters + (size_t)2 * pl.Gs * kCntStride + 48);
   P->rms_w = d->out_rms_weight; P->rms_eps = d->out_rms_eps;
+  P->post_gate = static_cast<const uint16_t*>(d->out_gate.ptr);
+  P->post_add = static_cast<const uint16_t*>(d->out_add.ptr);
+  P->pg_sb = d->out_gate.stride_b; P->pg_sh = d->out_gate.stride_h; P->pg_sm = d->out_gate.stride_m; P->pg_sw = d->out_gate.stride_w;
+  P->pa_sb = d->out_add.stride_b; P->pa_sh = d->out_add.stride_h; P->pa_sm = d->out_add.stride_m; P->pa_sw = d->out_add.stride_w;
+  P->g3_H = d->grid[1]; P->g3_W = d->grid[2];
   P->mix = d->mix; P->mix_ld = d->mix_ld; P->w_planes = Wp; P->Mp = pl.Mp; P->self_prep = 0;
   P->G = pl.Gs; P->H = d->H; P->M = pl.Ms; P->pack = pl.pack; P->M0 = d->M; P->w = d->w; P->TW = pl.TW; P->nsub = pl.nsub;
   P->ncols = pl.ncols; P->wpad = pl.wpad;
@@ -305,6 +311,7 @@ constexpr int kMaxDevices = 64;
 struct DeviceState {
   int sms = 0;          // 0: not queried yet; < 0: not an sm_100 device
   bool attr64 = false, attr128 = false, attr64g = false, attr128g = false, attr_smalln = false;
+  bool attr_post[4] = {false, false, false, false};   // POST instantiations: [D == 128][3-D view]
 };
 DeviceState g_dev[kMaxDevices];
 
@@ -335,7 +342,7 @@ std::vector<SmallNCacheEntry> g_smalln_cache;
 // Short sequences (DiT / ViT): the whole (b,h) unit fits one CTA - see smalln_kernel.cuh.
 bool smalln_eligible(const mhla_blockmix_desc* d) {
   if (d->D != 64 || d->M > mhla::kSnMaxM || (long long)d->M * d->w > mhla::kSnRows) return false;
-  if (d->q_rope.ptr || d->k_rope.ptr || d->out_rms_weight) return false;
+  if (d->q_rope.ptr || d->k_rope.ptr || d->out_rms_weight || d->out_gate.ptr) return false;
   if (d->grid[0] | d->grid[1] | d->grid[2] | d->layout[0] | d->layout[1] | d->layout[2]) return false;
   if (d->flags & (MHLA_FLAG_NO_SMALLN | MHLA_FLAG_UNFUSED | MHLA_FLAG_TWO_LAUNCH | MHLA_FLAG_FUSED | MHLA_FLAG_STOP_AFTER_P1 |
                   MHLA_FLAG_STOP_AFTER_P2 | MHLA_FLAG_ONLY_P3 | MHLA_FLAG_ONLY_P2))
@@ -364,6 +371,8 @@ int launch_smalln(const mhla_blockmix_desc* d, DeviceState* dst, cudaStream_t st
       P.normalize = (d->flags & MHLA_FLAG_NORMALIZE) ? 1 : 0;
       P.is_fp16 = d->dtype == MHLA_FP16;
       P.eps = d->eps;
+      P.post_add = static_cast<const uint16_t*>(d->out_add.ptr);
+      P.pa_sb = d->out_add.stride_b; P.pa_sh = d->out_add.stride_h; P.pa_sm = d->out_add.stride_m; P.pa_sw = d->out_add.stride_w;
       if (g_smalln_cache.size() >= 32) g_smalln_cache.erase(g_smalln_cache.begin());
       SmallNCacheEntry e;
       std::memcpy(&e.key, d, sizeof(*d));
@@ -450,6 +459,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   if (!small && (reinterpret_cast<uintptr_t>(d->workspace) & 1023) != 0) return MHLA_ERR_ALIGNMENT;
   if (!t5_ok(d->q) || !t5_ok(d->k) || !t5_ok(d->v) || !t5_ok(d->out)) return MHLA_ERR_ALIGNMENT;
   if (d->q_rope.ptr && (!t5_ok(d->q_rope) || !t5_ok(d->k_rope))) return MHLA_ERR_ALIGNMENT;
+  if ((d->out_gate.ptr && !t5_ok(d->out_gate)) || (d->out_add.ptr && !t5_ok(d->out_add))) return MHLA_ERR_ALIGNMENT;
   if (d->mix_ld < d->M) return MHLA_ERR_INVALID_ARGUMENT;
   if (pl.g3d) {   // token-major tensors: the batch must follow the token axis directly ((b, f) is ONE tensor-map dimension)
     const long long ntok = (long long)d->grid[0] * d->grid[1] * d->grid[2];
@@ -494,11 +504,17 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.o_hint = kn.o_hint;
   P.q_hint = kn.q_hint;
   P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = 0;   // (round-1 tuning options, fixed at their best values)
+  // fused gate / additive term: separate instantiations, so the plain kernels' code is untouched by them
+  const bool post = d->out_gate.ptr != nullptr || d->out_add.ptr != nullptr;
   auto kern = pl.g3d ? (d->D == 64 ? mhla::blockmix_kernel<64, true> : mhla::blockmix_kernel<128, true>)
                      : (d->D == 64 ? mhla::blockmix_kernel<64, false> : mhla::blockmix_kernel<128, false>);
+  if (post)
+    kern = pl.g3d ? (d->D == 64 ? mhla::blockmix_kernel<64, true, true> : mhla::blockmix_kernel<128, true, true>)
+                  : (d->D == 64 ? mhla::blockmix_kernel<64, false, true> : mhla::blockmix_kernel<128, false, true>);
   {
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    bool& attr = pl.g3d ? (d->D == 64 ? dst->attr64g : dst->attr128g) : (d->D == 64 ? dst->attr64 : dst->attr128);
+    bool& attr = post ? dst->attr_post[(d->D == 128 ? 2 : 0) + (pl.g3d ? 1 : 0)]
+                      : (pl.g3d ? (d->D == 64 ? dst->attr64g : dst->attr128g) : (d->D == 64 ? dst->attr64 : dst->attr128));
     if (!attr) {
       if (!cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, mhla::kSmemAlloc),
                    "cudaFuncSetAttribute"))
@@ -644,6 +660,51 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   else if (d->in_dtype == 1) mhla::wan_prep_kernel<1><<<grid, threads, 0, stream>>>(P);
   else mhla::wan_prep_kernel<2><<<grid, threads, 0, stream>>>(P);
   if (!cuda_ok(cudaGetLastError(), "wan_prep_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
+int mhla_bwd_prep(const mhla_bwd_prep_desc* d, void* stream_) {
+  if (!d || !d->dout || !d->out || !d->den || !d->dnum || !d->dden) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->rows < 1 || (d->D != 64 && d->D != 128)) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->dout) | reinterpret_cast<uintptr_t>(d->out) |
+                       reinterpret_cast<uintptr_t>(d->dnum);
+  if ((al & 15) != 0) return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::BwdPrepParams P{d->dout, d->out, d->den, d->dnum, d->dden, (long long)d->rows, d->D, d->dtype == MHLA_FP16};
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int tpr = d->D / 8, rpc = 256 / tpr;
+  const long long want = (d->rows + rpc - 1) / rpc, cap = (long long)dst->sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  if (tpr == 8) mhla::bwd_prep_kernel<8><<<grid, 256, 0, stream>>>(P);
+  else mhla::bwd_prep_kernel<16><<<grid, 256, 0, stream>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "bwd_prep_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
+int mhla_bwd_post(const mhla_bwd_post_desc* d, void* stream_) {
+  if (!d || !d->dnl || !d->ksum || !d->dksum || !d->dq || !d->dk) return MHLA_ERR_INVALID_ARGUMENT;
+  if ((d->dqn == nullptr) != (d->dkn == nullptr)) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->rows < 1 || d->w < 1 || d->rows % d->w != 0 || d->D < 8 || d->D % 8 != 0) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->dqn) | reinterpret_cast<uintptr_t>(d->dkn) |
+                       reinterpret_cast<uintptr_t>(d->dq) | reinterpret_cast<uintptr_t>(d->dk) |
+                       reinterpret_cast<uintptr_t>(d->ksum) | reinterpret_cast<uintptr_t>(d->dksum);
+  if ((al & 15) != 0) return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::BwdPostParams P{d->dqn, d->dkn, d->dnl, d->ksum, d->dksum, d->dq, d->dk, (long long)d->rows, d->w, d->D,
+                        d->dtype == MHLA_FP16};
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const long long want = ((long long)d->rows * (d->D / 8) + 255) / 256, cap = (long long)dst->sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  mhla::bwd_post_kernel<<<grid, 256, 0, stream>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "bwd_post_kernel")) return MHLA_ERR_CUDA;
   g_last_launches = 1;
   return MHLA_OK;
 }

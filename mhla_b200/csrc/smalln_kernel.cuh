@@ -45,6 +45,10 @@ struct alignas(64) SmallNParams {
   int normalize, is_fp16;
   float eps;
   unsigned long long* prof;         // optional [gridDim][16] cycle counters of warpgroup 0 (debug, tools/prof_smalln.py)
+  // fused "+ lepe" of the readout (mhla_dit/mhla/mhla.py:271-273; ABI v4 out_add): 16-bit tensor laid out like out with its
+  // own element strides, NULL = off.  Every epilogue thread adds its token row's 128 bytes before the rounding.
+  const uint16_t* post_add;
+  long long pa_sb, pa_sh, pa_sm, pa_sw;
 };
 
 __device__ __forceinline__ void tmem_st_x16(uint32_t taddr, const uint32_t (&r)[16]) {
@@ -287,19 +291,47 @@ __global__ void __launch_bounds__(kSnThreads, 1) smalln_kernel(const __grid_cons
         mbar_wait(&ofull[t], ph);
         lap(3);   // wait for O = A V
         tc_fence_after();
-        uint32_t v[32], v2[32], pk[32];
-        tmem_ld_x32(acc + 128, v);
-        tmem_ld_x32(acc + 160, v2);
-        tmem_ld_wait();
+        uint32_t pk[32];
+        if (p.post_add != nullptr) {
+          // fused additive term: 32 columns at a time, the row's 64-byte pieces of the add tensor read directly
+          const uint16_t* arow = p.post_add + (long long)(g / p.H) * p.pa_sb + (long long)(g % p.H) * p.pa_sh +
+                                 (long long)blk_t * p.pa_sm + (long long)pos_t * p.pa_sw;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
-          const float a = __uint_as_float(v[2 * e]) * rden, bq = __uint_as_float(v[2 * e + 1]) * rden;
-          const float c2 = __uint_as_float(v2[2 * e]) * rden, d2 = __uint_as_float(v2[2 * e + 1]) * rden;
-          if (p.is_fp16) {
-            __half2 h0 = __floats2half2_rn(a, bq), h1 = __floats2half2_rn(c2, d2);
-            pk[e] = *reinterpret_cast<uint32_t*>(&h0); pk[16 + e] = *reinterpret_cast<uint32_t*>(&h1);
-          } else {
-            pk[e] = pack_bf16x2(a, bq); pk[16 + e] = pack_bf16x2(c2, d2);
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t v[32], aw[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 a4 = make_uint4(0u, 0u, 0u, 0u);
+              if (row_ok) a4 = __ldg(reinterpret_cast<const uint4*>(arow + hh * 32) + i);
+              aw[4 * i] = a4.x; aw[4 * i + 1] = a4.y; aw[4 * i + 2] = a4.z; aw[4 * i + 3] = a4.w;
+            }
+            tmem_ld_x32(acc + 128 + hh * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              float2 a2;
+              if (p.is_fp16) a2 = __half22float2(*reinterpret_cast<const __half2*>(&aw[e]));
+              else a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
+              const float x0 = fmaf(__uint_as_float(v[2 * e]), rden, a2.x), x1 = fmaf(__uint_as_float(v[2 * e + 1]), rden, a2.y);
+              if (p.is_fp16) { __half2 h0 = __floats2half2_rn(x0, x1); pk[hh * 16 + e] = *reinterpret_cast<uint32_t*>(&h0); }
+              else pk[hh * 16 + e] = pack_bf16x2(x0, x1);
+            }
+          }
+        } else {
+          uint32_t v[32], v2[32];
+          tmem_ld_x32(acc + 128, v);
+          tmem_ld_x32(acc + 160, v2);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float a = __uint_as_float(v[2 * e]) * rden, bq = __uint_as_float(v[2 * e + 1]) * rden;
+            const float c2 = __uint_as_float(v2[2 * e]) * rden, d2 = __uint_as_float(v2[2 * e + 1]) * rden;
+            if (p.is_fp16) {
+              __half2 h0 = __floats2half2_rn(a, bq), h1 = __floats2half2_rn(c2, d2);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h0); pk[16 + e] = *reinterpret_cast<uint32_t*>(&h1);
+            } else {
+              pk[e] = pack_bf16x2(a, bq); pk[16 + e] = pack_bf16x2(c2, d2);
+            }
           }
         }
         uint4* dst = reinterpret_cast<uint4*>(st + row * 128);

@@ -50,6 +50,7 @@ class _MHLAImage(nn.Module):
             num_patches_per_side=int(self.embed_len ** 0.5), patch_group_size=bs, transform=transform,
             local_thres=kwargs.get("local_thres", 1.5), exp_sigma=kwargs.get("exp_sigma", 3))
         self.eps = kwargs.get("eps", 1e-6)
+        self.fuse_lepe = kwargs.get("fuse_lepe", True)   # extension: "+ lepe" inside the kernel's readout epilogue
         self.to_out = nn.Sequential(nn.Linear(inner_dim, dim), nn.Dropout(dropout))
         if fixed_weight_value is not None:
             self._init_weights_with_fixed_value(fixed_weight_value)
@@ -95,8 +96,14 @@ class _MHLAImage(nn.Module):
             # inference: the kernel writes straight into the "(b h) n w d -> b n w (h d)" layout (no head-merge copy)
             cdtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
             obuf = torch.empty((B, M, w, H, D), dtype=cdtype, device=x.device)
-            mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True, out=obuf.permute(0, 3, 1, 2, 4))   # mhla.py:262-268
-            out = obuf.view(B, M, w, H * D)
+            # "+ lepe" (mhla.py:271-273) rides in the readout epilogue: added in fp32 before the single rounding
+            add = lepe.reshape(B, M, w, H, D).permute(0, 3, 1, 2, 4) if self.fuse_lepe else None
+            mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True, out=obuf.permute(0, 3, 1, 2, 4), out_add=add)   # mhla.py:262-268
+            out = obuf.view(B, M, w, H * D).to(x.dtype)
+            if add is None:
+                out = out + lepe
+            out = self.to_out(out)
+            return out.view(B, M * w, -1) if squeeze else out
         else:
             # training (autograd through the operator) or a head dim the shim zero-pads (DiT-XL: 1152 / 16 = 72)
             o5 = mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True)

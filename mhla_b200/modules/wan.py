@@ -111,6 +111,7 @@ class _MHLAVideoBase(nn.Module):
         self.is_gated = gated
         self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: per-head g_norm inside the kernel epilogue
         self.fast_path = kwargs.get("fast_path", True)           # extension: fused pre-processing + 3-D block TMA view
+        self.fuse_post = kwargs.get("fuse_post", True)           # extension: SiLU gate and "+ lepe" in the kernel epilogue
         self.is_lepe = lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
@@ -166,21 +167,30 @@ class _MHLAVideoBase(nn.Module):
         v4 = (v if v.dtype == cdtype else v.to(cdtype)).view(B, N, nh, D)
         fuse = (dict(out_rms_weight=self.g_norm.weight, out_rms_eps=self.g_norm.eps)
                 if (self._gnorm == "head" and self.fuse_out_norm) else {})
+        # the SiLU gate and "+ lepe" ride in the same epilogue (out = g_norm(o) * silu(g(x)) + lepe in fp32, one rounding:
+        # mhla_utils.py:357-364, wan/model.py:1001-1003) whenever nothing un-fused sits between the operator and them
+        post = {}
+        if self.fuse_post and ((self._gnorm == "head" and fuse) or self._gnorm is None):
+            if self.is_gated:
+                post["out_gate"] = self.g(x).view(B, N, nh, D)
+            if self.is_lepe:
+                post["out_add"] = lepe.view(B, N, nh, D)
         Wm = self.block_attn.conv.weight
         if self.normalize_out:
             out = mhla_blockmix_grid(q_n, k_n, v4, Wm, grid, self.blocks_layout, q_rope=q_rope, k_rope=k_rope, eps=self.eps,
-                                     normalize=True, **fuse)
+                                     normalize=True, **fuse, **post)
         else:
-            out = mhla_blockmix_grid(q_rope, k_rope, v4, Wm, grid, self.blocks_layout, eps=self.eps, normalize=False, **fuse)
+            out = mhla_blockmix_grid(q_rope, k_rope, v4, Wm, grid, self.blocks_layout, eps=self.eps, normalize=False, **fuse,
+                                     **post)
         out = out.to(q.dtype)
         if self._gnorm == "head" and not fuse:
             out = self.g_norm(out)
         out = out.reshape(B, N, C)
         if self._gnorm == "dim":
             out = self.g_norm(out)
-        if self.is_gated:
+        if self.is_gated and "out_gate" not in post:
             out = out * self.g_fn(self.g(x))
-        if self.is_lepe:
+        if self.is_lepe and "out_add" not in post:
             out = out + lepe
         out = self.o(out)
         return self.out_rmsnorm(out) if self._out_norm else out
@@ -201,8 +211,9 @@ class _MHLAVideoBase(nn.Module):
         dtype = q.dtype
         W = self.block_attn.conv.weight
         training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)
-        if (self.fast_path and not training and x.is_cuda and D in (64, 128) and N == F_ * H_ * W_ and p2 * p3 <= 128
-                and -(-p1 // max(1, min(p1, 128 // (p2 * p3)))) <= 2):
+        view3d = (self.fast_path and x.is_cuda and D in (64, 128) and N == F_ * H_ * W_ and p2 * p3 <= 128
+                  and -(-p1 // max(1, min(p1, 128 // (p2 * p3)))) <= 2)   # the kernel's 3-D block view applies
+        if view3d and not training:
             return self._forward_fused(x, q, k, v, lepe, (F_, H_, W_), grid_sizes, freqs)
         q = torch.relu(self.norm_q(q.float())) + self.eps                          # :308, 267-276
         k = torch.relu(self.norm_k(k.float())) + self.eps
@@ -219,9 +230,15 @@ class _MHLAVideoBase(nn.Module):
         if self.normalize_out:
             out = mhla_blockmix(blk(q), blk(k), blk(v), W, q_rope=blk(q_rope), k_rope=blk(k_rope), eps=self.eps,
                                 normalize=True, **fuse)
+        elif training and view3d:
+            # training in the shipped configuration (norm_output: false): forward AND the three gradient launches gather /
+            # scatter the blocks by TMA (autograd.BlockmixGridFunction) - no block-major copies in either direction
+            out = mhla_blockmix_grid(q_rope.to(cdtype), k_rope.to(cdtype), v.to(cdtype), W, (F_, H_, W_), self.blocks_layout,
+                                     eps=self.eps, normalize=False).to(dtype)
         else:  # shipped Wan config (norm_output: false): the un-roped q/k are not needed at all
             out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), W, eps=self.eps, normalize=False, **fuse)
-        out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
+        if out.dim() == 5:
+            out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
         if self._gnorm == "head" and not fuse_norm:
             out = self.g_norm(out)                                                  # :360-364 per-head RMSNorm
         out = out.reshape(B, N, C)

@@ -71,6 +71,16 @@ class _Local(__import__("threading").local):
 _TLS = _Local()
 
 
+def _new_ws(device: torch.device, nbytes: int, off_cnt: int) -> torch.Tensor:
+    # only the control block (dependency counters, tickets, flags) has to start out zero - the kernel keeps it
+    # that way; zeroing just that keeps a CUDA-graph capture of the first call from recording a memset of the
+    # whole (tens of MB) workspace that every replay would repeat
+    ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    ws[base + off_cnt:].zero_()
+    return ws
+
+
 def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int, sig: tuple, off_cnt: int) -> torch.Tensor:
     # keyed by the full call signature: two shapes of equal total size lay the control block out differently
     key = (device.index, stream_handle, nbytes) + tuple(sig)
@@ -78,14 +88,20 @@ def _persistent_ws(device: torch.device, nbytes: int, stream_handle: int, sig: t
     if ws is None:
         if len(_WS_CACHE) >= _WS_CACHE_MAX:
             _WS_CACHE.pop(next(iter(_WS_CACHE)))
-        # only the control block (dependency counters, tickets, flags) has to start out zero - the kernel keeps it
-        # that way; zeroing just that keeps a CUDA-graph capture of the first call from recording a memset of the
-        # whole (tens of MB) workspace that every replay would repeat
-        ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
-        base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
-        ws[base + off_cnt:].zero_()
-        _WS_CACHE[key] = ws
+        ws = _WS_CACHE[key] = _new_ws(device, nbytes, off_cnt)
     return ws
+
+
+def _ws_views(ws: torch.Tensor, lay, G: int, M: int, D: int) -> dict:
+    """Typed views of a workspace (mhla_blockmix_workspace_layout): block summaries S [G, M, ncols] (D*D summaries, then
+    n_loc hi | lo), mixed summaries St [G, M, D*D] (16-bit, viewed as int16) and den [G, M, 2*wpad] fp32."""
+    base = (ws.data_ptr() + 1023) // 1024 * 1024 - ws.data_ptr()
+    ncols, wpad = int(lay[5]), int(lay[6])
+    return dict(
+        S=ws[base + lay[0]: base + lay[0] + G * M * ncols * 2].view(torch.int16).view(G, M, ncols),
+        St=ws[base + lay[1]: base + lay[1] + G * M * D * D * 2].view(torch.int16).view(G, M, D * D),
+        den=(ws[base + lay[2]: base + lay[2] + G * M * 2 * wpad * 4].view(torch.float32).view(G, M, 2 * wpad) if wpad else None),
+        ncols=ncols, wpad=wpad)
 
 
 def _t5(t: Optional[torch.Tensor]) -> _capi.Tensor5:
@@ -100,25 +116,28 @@ def _needs_grad(*tensors) -> bool:
 
 
 def mhla_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
-                  out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
+                  out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None,
+                  out_gate: Optional[torch.Tensor] = None, out_add: Optional[torch.Tensor] = None, **kw) -> torch.Tensor:
     """Non-causal block-mixed MHLA (see ``_blockmix_fwd`` for the arguments).  Differentiable: when gradients are
     enabled and an input requires them the call goes through ``autograd.BlockmixFunction`` (CUDA forward, analytic
     backward for q, k, v, q_rope, k_rope and the mixing matrix); ``out=`` and the fused output RMSNorm are
     inference-only and raise instead of silently dropping the graph."""
-    if _needs_grad(q, k, v, mix, q_rope, k_rope, out_rms_weight):
-        if out is not None or out_rms_weight is not None:
-            raise NotImplementedError("out= / out_rms_weight are inference-only; call without them when training")
+    if _needs_grad(q, k, v, mix, q_rope, k_rope, out_rms_weight, out_gate, out_add):
+        if out is not None or out_rms_weight is not None or out_gate is not None or out_add is not None:
+            raise NotImplementedError("out= and the fused epilogue (out_rms_weight / out_gate / out_add) are inference-only; "
+                                      "call without them when training")
         from .autograd import BlockmixFunction
         return BlockmixFunction.apply(q, k, v, mix, q_rope, k_rope, float(eps), bool(normalize), kw)
     return _blockmix_fwd(q, k, v, mix, q_rope=q_rope, k_rope=k_rope, eps=eps, normalize=normalize, out=out,
-                         out_rms_weight=out_rms_weight, **kw)
+                         out_rms_weight=out_rms_weight, out_gate=out_gate, out_add=out_add, **kw)
 
 
 def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                   out: Optional[torch.Tensor] = None, fused: bool = True, unfused: Optional[bool] = None,
                   three_launch: bool = False, two_launch: bool = False, force_fused: bool = False, debug_flags: int = 0,
                   out_rms_weight: Optional[torch.Tensor] = None, out_rms_eps: float = 1e-6,
-                  no_smalln: bool = False) -> torch.Tensor:
+                  no_smalln: bool = False, ws_out: Optional[dict] = None, out_gate: Optional[torch.Tensor] = None,
+                  out_add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Non-causal block-mixed MHLA forward on block-major tensors (no autograd graph).
 
     q, k, v : [B, H, M, w, D] (or the reference's [(B H), M, w, D]); bf16 / fp16 (fp32 is computed in bf16
@@ -128,11 +147,17 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     q_rope, k_rope : roped copies for the numerator (variant B); q, k then only feed the normaliser.
     out_rms_weight : optional [D] weight of a per-(token, head) RMSNorm fused into the readout epilogue
               (out = o * rsqrt(mean_d(o^2) + out_rms_eps) * weight; MHLA_Video_Uni's g_norm, mhla_utils.py:360-362).
+    out_gate, out_add : optional tensors shaped like the output (any TMA-compatible strides, e.g. permuted views of a
+              [B, M, w, H*D] projection): out = o * silu(out_gate) + out_add, fused into the readout epilogue in fp32 before
+              the single rounding (the SiLU gate and "+ lepe" of the Wan classes, the "+ lepe" of MHLA4DiT; ABI v4).
     no_smalln : units of at most 256 tokens (M*w <= 256, D = 64, M <= 64: DiT / ViT) normally take the short-sequence
               kernel (whole unit on chip, no workspace, csrc/smalln_kernel.cuh); True forces the general kernel.
     fused   : (default) one persistent kernel: items are scheduled at run time, cross-CTA dependencies go through
               per-group counters.  ``three_launch`` / ``unfused=True`` run the phases as three PDL-chained launches of
               the same kernel (an independent cross-check), ``two_launch`` as summaries+mixing followed by the readout.
+    ws_out  : optional dict; the call then runs on a PRIVATE workspace and fills the dict with typed views of it
+              (``_ws_views``: the block summaries S_j = k_j^T v_j the kernel produced) - the backward pass reads the
+              summaries of its own launches from there (autograd.py).  Left empty when the shape takes no workspace.
     """
     _require_cuda(q, k, v, mix, q_rope, k_rope)
     q, k, v = q.detach(), k.detach(), v.detach()
@@ -158,8 +183,8 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         D = 64 if D < 64 else 128
         padc = lambda t: None if t is None else torch.nn.functional.pad(t, (0, D - D_in))  # noqa: E731
         q5, k5, v5, qr5, kr5 = padc(q5), padc(k5), padc(v5), padc(qr5), padc(kr5)
-        if out_rms_weight is not None:
-            raise ValueError("out_rms_weight needs a head dim of 64 or 128 (the RMS would include the padding)")
+        if out_rms_weight is not None or out_gate is not None or out_add is not None:
+            raise ValueError("the fused epilogue (out_rms_weight / out_gate / out_add) needs a head dim of 64 or 128")
     mix2 = mix.reshape(mix.shape[0], mix.shape[1]) if mix.dim() != 2 else mix
     if tuple(mix2.shape) != (M, M):
         raise ValueError(f"mix must be [{M}, {M}], got {tuple(mix.shape)}")
@@ -183,7 +208,20 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         flags |= _capi.FLAG_WS_PERSISTENT | (_capi.FLAG_FUSED if force_fused else 0)
     L = _capi.lib()
     # the descriptor (shape, flags, workspace size) is cached per call signature; only pointers and strides change
-    sig = (B, H, M, w, D, cdtype, flags, float(eps), qr5 is not None, out_rms_weight is not None)
+    post = []
+    for name, t in (("out_gate", out_gate), ("out_add", out_add)):
+        if t is None:
+            post.append(None)
+            continue
+        t5 = _as5(t.detach())
+        if tuple(t5.shape) != (B, H, M, w, D):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected the output's {(B, H, M, w, D)}")
+        if t5.dtype != cdtype:
+            t5 = t5.to(cdtype)
+        post.append(t5 if _tma_ok(t5) else t5.contiguous())
+    g5, a5 = post
+    sig = (B, H, M, w, D, cdtype, flags, float(eps), qr5 is not None, out_rms_weight is not None, g5 is not None,
+           a5 is not None)
     cache = _TLS.desc
     ent = cache.get(sig)
     if ent is None:
@@ -199,15 +237,18 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
         # short sequences (no rope, no fused output norm) run without a workspace (csrc/smalln_kernel.cuh)
         d.q_rope.ptr, d.k_rope.ptr = (1 if qr5 is not None else None), (1 if kr5 is not None else None)
         d.out_rms_weight = 1 if out_rms_weight is not None else None
+        d.out_gate.ptr, d.out_add.ptr = (1 if g5 is not None else None), (1 if a5 is not None else None)
         needs_ws = bool(L.mhla_blockmix_needs_workspace(C.byref(d))) if hasattr(L, "mhla_blockmix_needs_workspace") else True
         lay = (C.c_size_t * 8)()
         _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
         if len(cache) > 64:
             cache.clear()
-        ent = cache[sig] = (d, nbytes, needs_ws, int(lay[4]))
-    d, nbytes, needs_ws, off_cnt = ent
+        ent = cache[sig] = (d, nbytes, needs_ws, tuple(int(x) for x in lay))
+    d, nbytes, needs_ws, lay = ent
+    off_cnt = lay[4]
     d.q, d.k, d.v, d.out = _t5(q5), _t5(k5), _t5(v5), _t5(o5)
     d.q_rope, d.k_rope = _t5(qr5), _t5(kr5)
+    d.out_gate, d.out_add = _t5(g5), _t5(a5)
     d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
     rms_w = None
     if out_rms_weight is not None:
@@ -219,11 +260,15 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
     if not needs_ws:
         d.workspace, d.workspace_bytes = None, 0
     else:
-        if single:
+        if single and ws_out is None:
             ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig, off_cnt)
+        elif single:
+            ws = _new_ws(q.device, nbytes, off_cnt)
         else:
             ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
         d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
+        if ws_out is not None:
+            ws_out.update(_ws_views(ws, lay, B * H, M, D), ws=ws, D=D)
     if torch.cuda.current_device() == q.device.index:
         _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
     else:
@@ -244,13 +289,32 @@ def _blockmix_fwd(q, k, v, mix, *, q_rope=None, k_rope=None, eps: float = 1e-6, 
 
 def mhla_blockmix_grid(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
                        out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None,
-                       out_rms_eps: float = 1e-6, three_launch: bool = False) -> torch.Tensor:
+                       out_rms_eps: float = 1e-6, three_launch: bool = False, ws_out: Optional[dict] = None,
+                       out_gate: Optional[torch.Tensor] = None, out_add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Block-mixed MHLA forward on TOKEN-major tensors with a 3-D block structure (variant B, Wan): q, k, v (and the
     roped copies) are [B, F*H*W, heads, D] - e.g. plain views of the q/k/v projections - and ``layout = (fb, hb, wb)``
     cuts the ``grid = (F, H, W)`` token grid into M = fb*hb*wb blocks of (F/fb)*(H/hb)*(W/wb) tokens, exactly the
     ``"b (fb p1 hb p2 wb p3) h c -> (b h) (fb hb wb) (p1 p2 p3) c"`` rearrangement of mhla_utils.py:317-326.  The kernel
     gathers the blocks with TMA boxes and scatters the output back (:345-354), so no block-major copy is ever made.
-    Returns [B, F*H*W, heads, D].  Inference path (no autograd graph)."""
+    Returns [B, F*H*W, heads, D].  Differentiable without the normaliser (``autograd.BlockmixGridFunction``: the shipped
+    Wan configuration); with it, training goes through the block-major ``mhla_blockmix``."""
+    if _needs_grad(q, k, v, mix, q_rope, k_rope, out_rms_weight, out_gate, out_add):
+        if (normalize or q_rope is not None or out is not None or out_rms_weight is not None or out_gate is not None
+                or out_add is not None):
+            raise NotImplementedError("the 3-D block view is differentiable for normalize=False without out= / fused "
+                                      "output norm (pass the roped q, k as q, k); use mhla_blockmix otherwise")
+        from .autograd import BlockmixGridFunction
+        return BlockmixGridFunction.apply(q, k, v, mix, tuple(grid), tuple(layout), float(eps))
+    return _blockmix_grid_fwd(q, k, v, mix, grid, layout, q_rope=q_rope, k_rope=k_rope, eps=eps, normalize=normalize, out=out,
+                              out_rms_weight=out_rms_weight, out_rms_eps=out_rms_eps, three_launch=three_launch, ws_out=ws_out,
+                              out_gate=out_gate, out_add=out_add)
+
+
+def _blockmix_grid_fwd(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, eps: float = 1e-6, normalize: bool = True,
+                       out: Optional[torch.Tensor] = None, out_rms_weight: Optional[torch.Tensor] = None,
+                       out_rms_eps: float = 1e-6, three_launch: bool = False, ws_out: Optional[dict] = None,
+                       out_gate: Optional[torch.Tensor] = None, out_add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``mhla_blockmix_grid`` without the autograd dispatch (``ws_out``: as in ``_blockmix_fwd``)."""
     _require_cuda(q, k, v, mix, q_rope, k_rope)
     if (q_rope is None) != (k_rope is None):
         raise ValueError("q_rope and k_rope must be given together")
@@ -277,6 +341,7 @@ def mhla_blockmix_grid(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, 
         return t if ok else t.contiguous()
 
     q4, k4, v4, qr4, kr4 = prep(q), prep(k), prep(v), prep(q_rope), prep(k_rope)
+    g4, a4 = prep(out_gate), prep(out_add)     # [B, N, heads, D] views of e.g. the gate projection / the LePE conv output
     o4 = torch.empty((B, N, nh, D), dtype=cdtype, device=q.device) if out is None else out
     if out is not None and (o4.dtype != cdtype or tuple(o4.shape) != (B, N, nh, D) or prep(o4) is not o4):
         raise ValueError("out must be a [B, N, heads, D] tensor of the compute dtype with TMA-compatible strides")
@@ -298,18 +363,23 @@ def mhla_blockmix_grid(q, k, v, mix, grid, layout, *, q_rope=None, k_rope=None, 
     lay = (C.c_size_t * 8)()
     _capi.check(L.mhla_blockmix_workspace_layout(C.byref(d), C.byref(lay)), "mhla_blockmix_workspace_layout")
     d.q, d.k, d.v, d.out, d.q_rope, d.k_rope = t5(q4), t5(k4), t5(v4), t5(o4), t5(qr4), t5(kr4)
+    d.out_gate, d.out_add = t5(g4), t5(a4)
     d.mix, d.mix_ld = mix2.data_ptr(), mix2.stride(0)
     rms_w = None
     if out_rms_weight is not None:
         rms_w = out_rms_weight.detach().to(device=q.device, dtype=torch.float32).contiguous()
     d.out_rms_weight, d.out_rms_eps = (rms_w.data_ptr() if rms_w is not None else None), float(out_rms_eps)
     stream = torch.cuda.current_stream(q.device)
-    sig = ("grid", B, nh, F_, H_, W_, fb, hb, wb, D, cdtype, flags, qr4 is not None)
+    sig = ("grid", B, nh, F_, H_, W_, fb, hb, wb, D, cdtype, flags, qr4 is not None, g4 is not None, a4 is not None)
     if three_launch:
         ws = torch.empty(nbytes + 1024, dtype=torch.uint8, device=q.device)
+    elif ws_out is not None:
+        ws = _new_ws(q.device, nbytes, int(lay[4]))
     else:
         ws = _persistent_ws(q.device, nbytes, stream.cuda_stream, sig, int(lay[4]))
     d.workspace, d.workspace_bytes = (ws.data_ptr() + 1023) // 1024 * 1024, nbytes
+    if ws_out is not None:
+        ws_out.update(_ws_views(ws, tuple(int(x) for x in lay), B * nh, M, D), ws=ws, D=D)
     with torch.cuda.device(q.device):
         _capi.check(L.mhla_fwd_blockmix(C.byref(d), stream.cuda_stream), "mhla_fwd_blockmix")
     return o4
@@ -351,6 +421,43 @@ def wan_prep(xq: torch.Tensor, xk: torch.Tensor, wq: Optional[torch.Tensor], wk:
     with torch.cuda.device(xq.device):
         _capi.check(_capi.lib().mhla_wan_prep(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_wan_prep")
     return qr, kr, qp, kp
+
+
+def bwd_prep(do: torch.Tensor, out: torch.Tensor, den: torch.Tensor):
+    """dnum = do / den[..., None] (16 bit) and dden = -(do . out) / den (fp32) in one pass over the token rows
+    (csrc/bwd_aux_kernel.cuh; ``mhla_bwd_prep``).  do, out: [..., D] 16-bit, den: [...] fp32; D in {64, 128}."""
+    _require_cuda(do, out, den)
+    D = do.shape[-1]
+    do, out = do.contiguous(), out.contiguous().to(do.dtype)
+    den = den.contiguous().to(torch.float32)
+    dnum = torch.empty_like(do)
+    dden = torch.empty_like(den)
+    d = _capi.BwdPrepDesc()
+    d.rows, d.D, d.dtype = do.numel() // D, D, _DT[do.dtype]
+    d.dout, d.out, d.den, d.dnum, d.dden = do.data_ptr(), out.data_ptr(), den.data_ptr(), dnum.data_ptr(), dden.data_ptr()
+    with torch.cuda.device(do.device):
+        _capi.check(_capi.lib().mhla_bwd_prep(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_bwd_prep")
+    return dnum, dden
+
+
+def bwd_post(dqn: Optional[torch.Tensor], dkn: Optional[torch.Tensor], dnl: torch.Tensor, ksum: torch.Tensor,
+             dksum: torch.Tensor, dtype: torch.dtype):
+    """dq = dqn + dnl[..., None] * ksum[..., None, :], dk = dkn + dksum[..., None, :] in one pass (``mhla_bwd_post``).
+    dqn, dkn: [..., M, w, D] 16-bit or None; dnl [..., M, w] fp32; ksum, dksum [..., M, D] fp32."""
+    _require_cuda(dnl, ksum, dksum, dqn, dkn)
+    w, D = dnl.shape[-1], ksum.shape[-1]
+    dnl, ksum, dksum = (t.contiguous().to(torch.float32) for t in (dnl, ksum, dksum))
+    if dqn is not None:
+        dqn, dkn = dqn.contiguous(), dkn.contiguous()
+    dq = torch.empty(tuple(dnl.shape) + (D,), dtype=dtype, device=dnl.device)
+    dk = torch.empty_like(dq)
+    d = _capi.BwdPostDesc()
+    d.rows, d.w, d.D, d.dtype = dnl.numel(), w, D, _DT[dtype]
+    d.dqn, d.dkn = (dqn.data_ptr(), dkn.data_ptr()) if dqn is not None else (None, None)
+    d.dnl, d.ksum, d.dksum, d.dq, d.dk = dnl.data_ptr(), ksum.data_ptr(), dksum.data_ptr(), dq.data_ptr(), dk.data_ptr()
+    with torch.cuda.device(dnl.device):
+        _capi.check(_capi.lib().mhla_bwd_post(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_bwd_post")
+    return dq, dk
 
 
 _HOST_STREAMS: "dict[int, tuple]" = {}

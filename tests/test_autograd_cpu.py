@@ -47,3 +47,71 @@ def test_causal_backward_matches_autograd(T, K, V):
         assert oracle.err_ratio(r, o) < 2e-5
     n = (T + 63) // 64
     assert float(got[3][n:].abs().max()) == 0.0 and float(got[3].triu(1).abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The GPU backward is a composition of FORWARD kernel launches with permuted / time-reversed operands
+# (autograd.blockmix_backward_native / causal_backward_native).  Here the launches are replaced by the oracle's forward
+# (float64), which checks the composition itself - operand order, W^T, time reversal, slicing of the value dim, the
+# summaries read back from the launches' workspaces - against torch.autograd of the oracle.
+def _stub_blockmix(q, k, v, mix, *, q_rope=None, k_rope=None, eps=1e-6, normalize=True, ws_out=None, **kw):
+    out = oracle.blockmix_fwd(q, k, v, mix, eps=eps, normalize=normalize, q_rope=q_rope, k_rope=k_rope, dtype=torch.float64)
+    if ws_out is not None:
+        kn = k if k_rope is None else k_rope
+        S = oracle.blockmix_summaries(kn.double(), v.double())            # [..., M, Dk, Dv], row-major like the workspace
+        M, D = S.shape[-3], S.shape[-1]
+        ws_out.update(S=S.reshape(-1, M, D * D), D=D)
+    return out
+
+
+def _stub_causal(q, k, v, mm, chunk_size=64, scale=None, **kw):
+    o = oracle.causal_chunk_fwd(q.double(), k.double(), v.double(), mm.double(), chunk_size=chunk_size, dtype=torch.float64)
+    return o * (float(scale) / q.shape[-1] ** -0.5)
+
+
+@pytest.mark.parametrize("normalize,rope,use_ws", [(True, False, True), (False, False, True), (True, True, True),
+                                                   (False, True, False)])
+def test_blockmix_backward_native_composition(monkeypatch, normalize, rope, use_ws):
+    from mhla_b200 import autograd, ops
+    monkeypatch.setitem(ops._DT, torch.float64, 0)
+    stub = _stub_blockmix if use_ws else (lambda *a, ws_out=None, **kw: _stub_blockmix(*a, **kw))
+    monkeypatch.setattr(ops, "_blockmix_fwd", stub)
+    g = torch.Generator().manual_seed(2)
+    G, M, w, D = 3, 5, 12, 16
+    mk = lambda relu: ((torch.relu(torch.randn(G, M, w, D, generator=g)) + 0.1) if relu  # noqa: E731
+                       else torch.randn(G, M, w, D, generator=g)).double().requires_grad_(True)
+    q, k, v = mk(True), mk(True), mk(False)
+    qr, kr = (mk(False), mk(False)) if rope else (None, None)
+    W = (torch.rand(M, M, generator=g) / M + 0.3 * torch.eye(M)).double().requires_grad_(True)
+    do = torch.randn(G, M, w, D, generator=g).double()
+    out = oracle.blockmix_fwd(q, k, v, W, eps=1e-6, normalize=normalize, q_rope=qr, k_rope=kr, dtype=torch.float64)
+    ins = [t for t in (q, k, v, W, qr, kr) if t is not None]
+    ref = torch.autograd.grad(out, ins, do, allow_unused=True)
+    d = lambda t: None if t is None else t.detach()   # noqa: E731
+    got = autograd.blockmix_backward_native(d(q), d(k), d(v), d(W), do, out.detach(), q_rope=d(qr), k_rope=d(kr), eps=1e-6,
+                                            normalize=normalize)
+    got = [g_ for g_, t in zip(got, (q, k, v, W, qr, kr)) if t is not None]
+    for r, o in zip(ref, got):
+        if r is None:
+            assert float(o.abs().max()) == 0.0
+            continue
+        assert oracle.err_ratio(r, o.double()) < 2e-6
+
+
+@pytest.mark.parametrize("T,K,V", [(128, 16, 24), (100, 8, 8), (192, 16, 160)])
+def test_causal_backward_native_composition(monkeypatch, T, K, V):
+    from mhla_b200 import autograd, ops
+    monkeypatch.setitem(ops._DT, torch.float64, 0)
+    monkeypatch.setattr(ops, "_causal_fwd", _stub_causal)
+    g = torch.Generator().manual_seed(3)
+    B, H, L = 2, 2, 32
+    q = torch.randn(B, T, H, K, generator=g).double().requires_grad_(True)
+    k = torch.randn(B, T, H, K, generator=g).double().requires_grad_(True)
+    v = torch.randn(B, T, H, V, generator=g).double().requires_grad_(True)
+    mm = torch.clamp(torch.rand(L, L, generator=g), 1e-5, 1).tril().double().requires_grad_(True)
+    do = torch.randn(B, T, H, V, generator=g).double()
+    out = oracle.causal_chunk_fwd(q, k, v, mm, dtype=torch.float64)
+    ref = torch.autograd.grad(out, [q, k, v, mm], do)
+    got = autograd.causal_backward_native(q.detach(), k.detach(), v.detach(), mm.detach(), do)
+    for r, o in zip(ref, got):
+        assert oracle.err_ratio(r, o.double()) < 1e-6

@@ -329,3 +329,72 @@ def test_blockmix_3d_block_view(B, nh, D, grid, layout, normalize, rope, three_l
         out2 = mhla_b200.mhla_blockmix_grid(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], W.cuda(), grid, layout,
                                             normalize=normalize, three_launch=three_launch)
         assert torch.equal(out2, out)
+
+
+def _post(ref, gate, add, wgt=None, eps=1e-5):
+    """out = (o [rms-normed per row, * wgt]) * silu(gate) + add in fp32 (mhla_utils.py:357-364)."""
+    if wgt is not None:
+        ref = ref * torch.rsqrt(ref.pow(2).mean(dim=-1, keepdim=True) + eps) * wgt
+    if gate is not None:
+        ref = ref * torch.nn.functional.silu(gate.float())
+    if add is not None:
+        ref = ref + add.float()
+    return ref
+
+
+@pytest.mark.parametrize("B,H,M,w,D,normalize,rms,gate,add", [
+    (2, 2, 8, 256, 64, True, False, True, True),      # general kernel, D = 64
+    (1, 2, 20, 210, 128, False, True, True, True),    # Wan block shape, per-head norm + gate + lepe
+    (1, 2, 20, 210, 128, True, False, False, True),   # additive term only
+    (2, 6, 16, 16, 64, True, False, False, True),     # DiT-S/2: "+ lepe" inside the short-sequence kernel
+    (3, 2, 4, 49, 64, True, False, False, True),      # ... ragged second row tile
+    (2, 6, 16, 16, 64, True, False, True, True),      # a gate at a short-sequence shape takes the general kernel
+])
+def test_blockmix_fused_gate_and_add(B, H, M, w, D, normalize, rms, gate, add):
+    """ABI v4 post-ops of the readout epilogue: out = o * silu(out_gate) + out_add (after the optional per-head RMS norm),
+    the gate / add tensors being permuted views of [B, M, w, H*D] tensors (as the modules pass them)."""
+    q, k, v, _, _ = _inputs(B, H, M, w, D, torch.bfloat16, seed=21)
+    g = torch.Generator().manual_seed(22)
+    W = torch.rand(M, M, generator=g) / M
+    wgt = (torch.rand(D, generator=g) + 0.5) if rms else None
+    gt = torch.randn(B, M, w, H * D, generator=g).bfloat16() if gate else None
+    ad = torch.randn(B, M, w, H * D, generator=g).bfloat16() if add else None
+    view = lambda t: None if t is None else t.cuda().view(B, M, w, H, D).permute(0, 3, 1, 2, 4)   # noqa: E731
+    kw = dict(out_rms_weight=wgt.cuda(), out_rms_eps=1e-5) if rms else {}
+    out = _run(q, k, v, W, normalize=normalize, out_gate=view(gt), out_add=view(ad), **kw)
+    ref = oracle.blockmix_fwd(q, k, v, W, normalize=normalize)
+    cpuview = lambda t: None if t is None else t.view(B, M, w, H, D).permute(0, 3, 1, 2, 4)   # noqa: E731
+    ref = _post(ref, cpuview(gt), cpuview(ad), wgt)
+    _check(ref, out, torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,nh,D,grid,layout,normalize", [
+    (1, 2, 128, (7, 12, 10), (1, 2, 2), False),     # Wan's block shape (two sub-tiles, ragged tail)
+    (2, 2, 128, (14, 6, 10), (2, 1, 2), True),      # batch 2, with the normaliser
+    (1, 2, 64, (8, 4, 4), (2, 2, 2), True),         # D = 64
+])
+def test_blockmix_3d_block_view_fused_gate_and_add(B, nh, D, grid, layout, normalize):
+    """Token-major 3-D block view with the fused per-head norm, SiLU gate and additive term: gate / add are plain
+    [B, N, heads*D] projection-shaped tensors viewed as [B, N, heads, D] (what MHLA_Video_Uni._forward_fused passes)."""
+    import mhla_b200
+    from einops import rearrange
+    F_, H_, W_ = grid
+    fb, hb, wb = layout
+    p1, p2, p3 = F_ // fb, H_ // hb, W_ // wb
+    N, M = F_ * H_ * W_, fb * hb * wb
+    g = torch.Generator().manual_seed(23)
+    mk = lambda relu: ((torch.relu(torch.randn(B, N, nh, D, generator=g)) + 1e-6) if relu  # noqa: E731
+                       else torch.randn(B, N, nh, D, generator=g)).bfloat16()
+    q, k, v, gt, ad = mk(True), mk(True), mk(False), mk(False), mk(False)
+    W = torch.rand(M, M, generator=g) / M + 0.5 * torch.eye(M) / M
+    wgt = torch.rand(D, generator=g) + 0.5
+    out = mhla_b200.mhla_blockmix_grid(q.cuda(), k.cuda(), v.cuda(), W.cuda(), grid, layout, normalize=normalize,
+                                       out_rms_weight=wgt.cuda(), out_rms_eps=1e-5, out_gate=gt.cuda(), out_add=ad.cuda())
+    torch.cuda.synchronize()
+    pat = "b (fb p1 hb p2 wb p3) h d -> b h (fb hb wb) (p1 p2 p3) d"
+    kw = dict(fb=fb, hb=hb, wb=wb, p1=p1, p2=p2, p3=p3)
+    blk = lambda t: rearrange(t, pat, **kw)  # noqa: E731
+    ref = oracle.blockmix_fwd(blk(q), blk(k), blk(v), W, normalize=normalize)
+    ref = rearrange(ref, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw)
+    ref = _post(ref, gt, ad, wgt)
+    _check(ref, out, torch.bfloat16)

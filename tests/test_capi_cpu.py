@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [n for n in names if not hasattr(L, n)]
     assert not missing, missing
     assert set(_capi.EXPORTS) <= set(names)
-    assert L.mhla_abi_version() == 3
+    assert L.mhla_abi_version() == 4
 
 
 def test_status_strings():

@@ -217,7 +217,8 @@ def test_wan_prep_kernel_matches_reference_preprocessing(in_dtype, plain):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("normalize_out,gated,lepe", [(False, False, False), (True, True, False), (True, False, True)])
+@pytest.mark.parametrize("normalize_out,gated,lepe", [(False, False, False), (True, True, False), (True, False, True),
+                                                      (False, True, True)])
 def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated, lepe):
     """MHLA_Video_Uni at Wan's block shape (7*6*5 = 210 tokens per block, D = 128): the fused inference path (one
     pre-processing launch + the 3-D block view) against the module's own reference-style path (torch pre-processing +
@@ -236,3 +237,29 @@ def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated,
         m.fast_path = False
         y_slow = m(x, torch.tensor([N, N]), gs, freqs)
     assert oracle.err_ratio(y_slow.float().cpu(), y_fast.float().cpu()) < 1.5e-2
+
+
+@pytest.mark.gpu
+def test_wan_module_training_step_through_the_3d_block_view():
+    """Training in the shipped Wan configuration (norm_output: false): forward and the three gradient launches of
+    autograd.BlockmixGridFunction gather / scatter the blocks by TMA.  Gradients of the projections and of the mixing
+    matrix against the module's block-major path (rearrange copies + BlockmixFunction) on the same weights."""
+    torch.manual_seed(4)
+    dim, heads, layout, grid = 256, 2, (1, 2, 2), (7, 12, 10)
+    N = grid[0] * grid[1] * grid[2]
+    m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=False).cuda().train()
+    x = torch.randn(2, N, dim, device="cuda")
+    gs = torch.tensor([list(grid)] * 2, dtype=torch.long)
+    freqs = oracle.rope_freqs_wan(dim // heads)
+    grads = []
+    for fast in (True, False):
+        m.fast_path = fast
+        m.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = m(x, torch.tensor([N, N]), gs, freqs)
+        y.float().square().mean().backward()
+        grads.append([p.grad.detach().float().cpu().clone() for p in (m.q.weight, m.k.weight, m.v.weight,
+                                                                       m.block_attn.conv.weight)])
+    for a, b in zip(*grads):
+        assert float(b.abs().max()) > 0
+        assert oracle.err_ratio(b, a) < 2e-2
