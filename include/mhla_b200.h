@@ -213,8 +213,33 @@ typedef struct mhla_bwd_post_desc {
   const float* ksum; const float* dksum; /* [rows / w, D] fp32 */
   void* dq; void* dk;                 /* [rows, D] 16-bit, written (may alias dqn / dkn) */
 } mhla_bwd_post_desc;
+/* out[b, :] = sum_t wgt[b, t] * x[b, t, :] over the w token rows of every block (wgt NULL: plain sums): ksum_j = sum_t
+ * k_{j,t} (mhla.py:265) and its gradient partner dksum_j = sum_t dnl[j,t] q_{j,t}.  x: [blocks, w, D] 16-bit contiguous,
+ * wgt: [blocks, w] fp32 or NULL, out: [blocks, D] fp32; D in {64, 128}. */
+typedef struct mhla_block_wsum_desc {
+  int64_t blocks; int32_t w, D, dtype;
+  const void* x; const float* wgt; float* out;
+} mhla_block_wsum_desc;
+int mhla_block_wsum(const mhla_block_wsum_desc* desc, void* stream);
 int mhla_bwd_prep(const mhla_bwd_prep_desc* desc, void* stream);
 int mhla_bwd_post(const mhla_bwd_post_desc* desc, void* stream);
+
+/*
+ * Post-op of the NLP layer: FusedRMSNormGated(o, g) (mhla_nlp/fla/modules/fused_norm_gate.py:77-99,
+ * called at mhla_nlp/fla/layers/mhla.py:350-356) per (token, head) row of the causal operator's output, one pass:
+ *   out[r, :] = x[r, :] * rsqrt(mean(x[r, :]^2) + eps) * weight * g[r, :] * sigmoid(g[r, :])
+ * x, g: [rows, D] 16-bit with row pitches ld_x / ld_g (elements); out: [rows, D] contiguous; weight fp32 [D] or NULL;
+ * g == NULL: plain RMSNorm (layers/mhla.py:358-360).  D in {64, 128, 256}.
+ */
+typedef struct mhla_gated_rmsnorm_desc {
+  int64_t rows; int32_t D; int32_t dtype;
+  const void* x; int64_t ld_x;
+  const void* g; int64_t ld_g;
+  const float* weight;
+  float eps;
+  void* out;
+} mhla_gated_rmsnorm_desc;
+int mhla_gated_rmsnorm(const mhla_gated_rmsnorm_desc* desc, void* stream);
 
 /* Misc. */
 int mhla_abi_version(void);

@@ -105,7 +105,7 @@ def blockmix_backward_native(q, k, v, W, do, out, *, q_rope=None, k_rope=None, e
     aux = q.is_cuda and D in (64, 128) and cd in (torch.bfloat16, torch.float16)   # csrc/bwd_aux_kernel.cuh
     ksum = dden = None
     if normalize:
-        ksum = k.sum(dim=-2, dtype=f)                                       # [..., M, D]
+        ksum = ops.block_wsum(c(k)) if aux else k.sum(dim=-2, dtype=f)      # [..., M, D]
         if den is None or nl is None:
             nl = torch.einsum("...jtd,...jd->...jt", q.to(f), ksum)         # [..., M, w]
             den = torch.einsum("ij,...jt->...it", Wf, nl) + eps
@@ -137,10 +137,7 @@ def blockmix_backward_native(q, k, v, W, do, out, *, q_rope=None, k_rope=None, e
     if normalize:
         dnl = torch.einsum("ij,...it->...jt", Wf, dden)                     # [..., M, w]
         if aux:
-            # sum_t dnl[j, t] q[j, t, :]: a [1 x w] . [w x D] product per block, hi + lo parts of dnl in the 16-bit dtype
-            hi = dnl.to(cd)
-            lo = (dnl - hi.to(f)).to(cd)
-            dksum = torch.matmul(torch.stack((hi, lo), dim=-2), c(q)).to(f).sum(dim=-2)
+            dksum = ops.block_wsum(c(q), dnl)                                # sum_t dnl[j, t] q[j, t, :]
             rope = q_rope is not None
             dq, dk = ops.bwd_post(None if rope else dQn, None if rope else dKn, dnl, ksum, dksum, cd)
             return (dq, dk, dV, dW, dQn, dKn) if rope else (dq, dk, dV, dW, None, None)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmhla_b200.so")
 SOURCES = ["mhla_capi.cu"]
-HEADERS = ["ptx.cuh", "blockmix_kernel.cuh", "causal_kernel.cuh", "smalln_kernel.cuh", "wan_prep_kernel.cuh", "bwd_aux_kernel.cuh", os.path.join("..", "..", "include", "mhla_b200.h")]
+HEADERS = ["ptx.cuh", "blockmix_kernel.cuh", "causal_kernel.cuh", "smalln_kernel.cuh", "wan_prep_kernel.cuh", "bwd_aux_kernel.cuh", "gated_norm_kernel.cuh", os.path.join("..", "..", "include", "mhla_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "--use_fast_math",

@@ -114,4 +114,43 @@ __global__ void __launch_bounds__(256) bwd_post_kernel(const BwdPostParams p) {
   }
 }
 
+// Per-block (weighted) column sums over the token axis: out[blk, :] = sum_t wgt[blk, t] * x[blk, t, :]  (wgt NULL: 1).
+//   ksum_j = sum_t k_{j,t}            (mhla.py:265)            dksum_j = sum_t dnl[j, t] q_{j,t}   (its gradient w.r.t. ksum)
+// One CTA per block at a time (grid-stride), 256 threads = (256 / (D/8)) token rows x (D/8) channel groups of 8.
+struct BlockSumParams {
+  const void* x;        // [blocks, w, D] 16-bit
+  const float* wgt;     // [blocks, w] or NULL
+  float* out;           // [blocks, D]
+  long long blocks;
+  int w, D, fp16;
+};
+
+__global__ void __launch_bounds__(256) block_wsum_kernel(const BlockSumParams p) {
+  __shared__ float red[32][129];
+  const int tpr = p.D / 8, rpc = 256 / tpr;
+  const int sub = threadIdx.x % tpr, rl = threadIdx.x / tpr;
+  for (long long blk = blockIdx.x; blk < p.blocks; blk += gridDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const long long base = blk * p.w;
+    for (int t = rl; t < p.w; t += rpc) {
+      float a[8];
+      aux_load8(p.x, (base + t) * p.D + sub * 8, p.fp16, a);
+      const float wv = p.wgt ? __ldg(p.wgt + base + t) : 1.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(wv, a[i], acc[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[rl][sub * 8 + i] = acc[i];
+    __syncthreads();
+    if ((int)threadIdx.x < p.D) {
+      float s = 0.f;
+      for (int r = 0; r < rpc; ++r) s += red[r][threadIdx.x];
+      p.out[blk * p.D + threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace mhla

@@ -17,6 +17,7 @@
 #include "smalln_kernel.cuh"
 #include "wan_prep_kernel.cuh"
 #include "bwd_aux_kernel.cuh"
+#include "gated_norm_kernel.cuh"
 
 namespace {
 
@@ -664,6 +665,30 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   return MHLA_OK;
 }
 
+int mhla_gated_rmsnorm(const mhla_gated_rmsnorm_desc* d, void* stream_) {
+  if (!d || !d->x || !d->out) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->rows < 1 || (d->D != 64 && d->D != 128 && d->D != 256)) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->g) | reinterpret_cast<uintptr_t>(d->out);
+  if ((al & 15) != 0 || d->ld_x % 8 != 0 || (d->g && d->ld_g % 8 != 0) || d->ld_x < d->D || (d->g && d->ld_g < d->D))
+    return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::GatedNormParams P{d->x, d->g, d->out, d->weight, (long long)d->rows, (long long)d->ld_x, (long long)d->ld_g, d->D,
+                          d->dtype == MHLA_FP16, d->eps};
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  const int tpr = d->D / 8, rpc = 256 / tpr;
+  const long long want = (d->rows + rpc - 1) / rpc, cap = (long long)dst->sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  if (tpr == 8) mhla::gated_norm_kernel<8><<<grid, 256, 0, stream>>>(P);
+  else if (tpr == 16) mhla::gated_norm_kernel<16><<<grid, 256, 0, stream>>>(P);
+  else mhla::gated_norm_kernel<32><<<grid, 256, 0, stream>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "gated_norm_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
 int mhla_bwd_prep(const mhla_bwd_prep_desc* d, void* stream_) {
   if (!d || !d->dout || !d->out || !d->den || !d->dnum || !d->dden) return MHLA_ERR_INVALID_ARGUMENT;
   if (d->rows < 1 || (d->D != 64 && d->D != 128)) return MHLA_ERR_UNSUPPORTED_SHAPE;
@@ -682,6 +707,23 @@ int mhla_bwd_prep(const mhla_bwd_prep_desc* d, void* stream_) {
   if (tpr == 8) mhla::bwd_prep_kernel<8><<<grid, 256, 0, stream>>>(P);
   else mhla::bwd_prep_kernel<16><<<grid, 256, 0, stream>>>(P);
   if (!cuda_ok(cudaGetLastError(), "bwd_prep_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
+int mhla_block_wsum(const mhla_block_wsum_desc* d, void* stream_) {
+  if (!d || !d->x || !d->out) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->blocks < 1 || d->w < 1 || (d->D != 64 && d->D != 128)) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  if ((reinterpret_cast<uintptr_t>(d->x) & 15) != 0) return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::BlockSumParams P{d->x, d->wgt, d->out, (long long)d->blocks, d->w, d->D, d->dtype == MHLA_FP16};
+  const long long cap = (long long)dst->sms * 8;
+  const int grid = (int)(d->blocks < cap ? d->blocks : cap);
+  mhla::block_wsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "block_wsum_kernel")) return MHLA_ERR_CUDA;
   g_last_launches = 1;
   return MHLA_OK;
 }

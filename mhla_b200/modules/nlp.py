@@ -112,6 +112,12 @@ class FusedRMSNormGated(RMSNorm):
     """y = rmsnorm(x) * weight * g * sigmoid(g)  (activation 'swish')."""
 
     def forward(self, x, g):
+        needs_grad = torch.is_grad_enabled() and (x.requires_grad or g.requires_grad or
+                                                  (self.weight is not None and self.weight.requires_grad))
+        if (x.is_cuda and not needs_grad and x.dtype in (torch.bfloat16, torch.float16)
+                and x.shape[-1] in (64, 128, 256) and g.shape == x.shape):
+            from ..ops import gated_rmsnorm      # one launch: csrc/gated_norm_kernel.cuh
+            return gated_rmsnorm(x, g, self.weight, self.eps)
         y = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + self.eps)
         if self.weight is not None:
             y = y * self.weight.float()

@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "gated_rmsnorm", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -421,6 +421,51 @@ def wan_prep(xq: torch.Tensor, xk: torch.Tensor, wq: Optional[torch.Tensor], wk:
     with torch.cuda.device(xq.device):
         _capi.check(_capi.lib().mhla_wan_prep(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_wan_prep")
     return qr, kr, qp, kp
+
+
+def gated_rmsnorm(x: torch.Tensor, g: Optional[torch.Tensor], weight: Optional[torch.Tensor], eps: float = 1e-5) -> torch.Tensor:
+    """y = x * rsqrt(mean(x^2, -1) + eps) * weight * g * sigmoid(g) per row of the last dim, one launch
+    (csrc/gated_norm_kernel.cuh; FusedRMSNormGated of the NLP layer, fla/modules/fused_norm_gate.py:77-99 as called at
+    layers/mhla.py:350-356).  ``g=None``: plain RMSNorm.  x, g: [..., D] bf16 / fp16 CUDA tensors, D in {64, 128, 256};
+    Inference only."""
+    _require_cuda(x, g, weight)
+    D = x.shape[-1]
+    if x.dtype not in _DT or D not in (64, 128, 256):
+        raise ValueError("gated_rmsnorm needs a bf16 / fp16 tensor with a last dim of 64, 128 or 256")
+
+    def rows(t):   # [rows, D]; a ragged / padded operator output (sliced view) is made contiguous first
+        t = t.detach()
+        if t.dtype != x.dtype:
+            t = t.to(x.dtype)
+        return t.contiguous().view(-1, D)
+    x2 = rows(x)
+    g2 = rows(g) if g is not None else None
+    out = torch.empty(tuple(x.shape), dtype=x.dtype, device=x.device)
+    d = _capi.GatedNormDesc()
+    d.rows, d.D, d.dtype = x2.shape[0], D, _DT[x.dtype]
+    d.x, d.ld_x = x2.data_ptr(), x2.stride(0)
+    d.g, d.ld_g = (g2.data_ptr(), g2.stride(0)) if g2 is not None else (None, 0)
+    wf = None if weight is None else weight.detach().to(device=x.device, dtype=torch.float32).contiguous()
+    d.weight, d.eps, d.out = (wf.data_ptr() if wf is not None else None), float(eps), out.data_ptr()
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().mhla_gated_rmsnorm(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_gated_rmsnorm")
+    return out
+
+
+def block_wsum(x: torch.Tensor, wgt: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[..., :] = sum_t wgt[..., t] * x[..., t, :] over the token axis of every block (``mhla_block_wsum``): x [..., w, D]
+    16-bit, wgt [..., w] fp32 or None (plain sums) -> [..., D] fp32.  ksum and its gradient partner of the backward pass."""
+    _require_cuda(x, wgt)
+    w, D = x.shape[-2], x.shape[-1]
+    x = x.contiguous()
+    out = torch.empty(tuple(x.shape[:-2]) + (D,), dtype=torch.float32, device=x.device)
+    d = _capi.BlockWsumDesc()
+    d.blocks, d.w, d.D, d.dtype = x.numel() // (w * D), w, D, _DT[x.dtype]
+    wf = None if wgt is None else wgt.contiguous().to(torch.float32)
+    d.x, d.wgt, d.out = x.data_ptr(), (wf.data_ptr() if wf is not None else None), out.data_ptr()
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().mhla_block_wsum(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_block_wsum")
+    return out
 
 
 def bwd_prep(do: torch.Tensor, out: torch.Tensor, den: torch.Tensor):

@@ -194,3 +194,21 @@ def test_causal_backward_through_the_kernel():
     out.backward(do.cuda().to(out.dtype))
     for ref, got in ((qc.grad, qg.grad), (kc.grad, kg.grad), (vc.grad, vg.grad), (mc.grad, mg.grad)):
         assert oracle.err_ratio(ref, got.float().cpu()) < 2e-2
+
+
+@pytest.mark.parametrize("D,gated,dtype", [(256, True, torch.bfloat16), (128, True, torch.float16), (64, False, torch.bfloat16)])
+def test_gated_rmsnorm_kernel(D, gated, dtype):
+    """csrc/gated_norm_kernel.cuh against FusedRMSNormGated's formula (fla/modules/fused_norm_gate.py:77-99):
+    y = rmsnorm_D(o) * w * g * sigmoid(g) per (token, head) row, fp32 math, one rounding."""
+    import mhla_b200
+    g_ = torch.Generator().manual_seed(31)
+    x = torch.randn(3, 100, 4, D, generator=g_).to(dtype)
+    gate = torch.randn(3, 100, 4, D, generator=g_).to(dtype) if gated else None
+    w = torch.rand(D, generator=g_) + 0.5
+    y = mhla_b200.gated_rmsnorm(x.cuda(), None if gate is None else gate.cuda(), w.cuda(), 1e-5)
+    torch.cuda.synchronize()
+    ref = x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-5) * w
+    if gated:
+        ref = ref * gate.float() * torch.sigmoid(gate.float())
+    tol = 3e-3 if dtype == torch.bfloat16 else 5e-4
+    assert oracle.err_ratio(ref, y.float().cpu()) < tol

@@ -58,3 +58,36 @@ for B, norm in ((1, False), (2, False), (2, True)):
     err = float((y1.float() - y2.float()).norm() / y2.float().norm())
     print(f"B={B} normalize_out={norm}: module forward fused {t_fast:.0f} us vs reference-style {t_slow:.0f} us "
           f"({t_slow / t_fast:.2f}x), rel diff {err:.2e}; operator (3-D view, no norm) {t_op:.0f} us, prep kernel {t_prep:.0f} us")
+
+# gate + LePE (MHLA_Video_Uni(is_gated, is_lepe) = Gated_MHLA_Video_LePE's post-processing): SiLU gate and "+ lepe" inside
+# the readout epilogue (ABI v4) against the same fused path with those two as separate elementwise passes
+m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=False, is_gated=True, is_lepe=True).cuda().eval()
+x = torch.randn(1, N, dim, device="cuda")
+gs, sl = torch.tensor([list(grid)], dtype=torch.long), torch.tensor([N])
+with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+    m.fuse_post = True
+    t_f = timed(lambda: m(x, sl, gs, freqs))
+    y1 = m(x, sl, gs, freqs)
+    m.fuse_post = False
+    t_u = timed(lambda: m(x, sl, gs, freqs))
+    y2 = m(x, sl, gs, freqs)
+print(f"B=1 gated + lepe layer: epilogue-fused gate/lepe {t_f:.0f} us vs separate passes {t_u:.0f} us, rel diff "
+      f"{float((y1.float() - y2.float()).norm() / y2.float().norm()):.2e}")
+
+# training step (forward + backward of the whole layer, bf16 autocast) in the shipped configuration: 3-D block view with
+# the native backward (autograd.BlockmixGridFunction) against the block-major path (rearrange copies + BlockmixFunction)
+m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=False).cuda().train()
+
+
+def train_step():
+    m.zero_grad(set_to_none=True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = m(x, sl, gs, freqs)
+    y.float().square().mean().backward()
+
+
+m.fast_path = True
+t_g = timed(train_step, reps=5)
+m.fast_path = False
+t_b = timed(train_step, reps=5)
+print(f"B=1 training step of the layer: 3-D block view {t_g:.0f} us vs block-major copies {t_b:.0f} us")
