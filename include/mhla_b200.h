@@ -241,6 +241,21 @@ typedef struct mhla_gated_rmsnorm_desc {
 } mhla_gated_rmsnorm_desc;
 int mhla_gated_rmsnorm(const mhla_gated_rmsnorm_desc* desc, void* stream);
 
+/*
+ * Post-ops of the Wan / DiT layers behind the block-mixed operator (SiLU gate and "+ lepe",
+ * mhla_videogen/diffusion/model/wan/mhla_utils.py:360-366, wan/model.py:1001-1003, mhla_dit/mhla/mhla.py:268-273), one
+ * streaming pass:   out[r, :] = x[r, :] * silu(g[r, :]) + add[r, :]     (g == NULL: no gate; add == NULL: nothing added)
+ * x, g, add, out: [rows, C] 16-bit, contiguous along C (C % 8 == 0), row pitches ld_* in elements; out may alias x.
+ */
+typedef struct mhla_gate_add_desc {
+  int64_t rows; int32_t C; int32_t dtype;
+  const void* x; int64_t ld_x;
+  const void* g; int64_t ld_g;
+  const void* add; int64_t ld_add;
+  void* out; int64_t ld_out;
+} mhla_gate_add_desc;
+int mhla_gate_add(const mhla_gate_add_desc* desc, void* stream);
+
 /* Misc. */
 int mhla_abi_version(void);
 const char* mhla_strerror(int status);

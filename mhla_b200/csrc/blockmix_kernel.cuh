@@ -22,6 +22,24 @@
 #include <type_traits>
 #include "ptx.cuh"
 
+// Early hand-back of the accumulator buffer to the tcgen05 issuer (measured on the headline shape, profiles/r02c_ab_early.log:
+// 142.6 -> 140.5 us): a P1 epilogue reads its whole accumulator (64 S columns + ksum, D = 64) into registers FIRST and
+// releases the buffer before the n_loc dot products and the staging of S (MHLA_EARLY_P1); a readout epilogue releases it
+// right after its last TMEM read, before the last tile is staged and stored (MHLA_EARLY_P3 = 2; = 1 holds both 64-column
+// halves in registers and releases before any staging - slower, register pressure; = 0: release at the end of the item).
+#ifndef MHLA_EARLY_P1
+#define MHLA_EARLY_P1 1
+#endif
+#ifndef MHLA_EARLY_P3
+#define MHLA_EARLY_P3 2
+#endif
+#ifndef MHLA_STATIC_FIRST
+#define MHLA_STATIC_FIRST 0
+#endif
+#ifndef MHLA_EPI_POLL1
+#define MHLA_EPI_POLL1 0
+#endif
+
 namespace mhla {
 
 constexpr int kStageBytes = 32768;
@@ -733,6 +751,19 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #endif
       uint32_t wg_load[2] = {0, 0};   // epilogue work handed to each warpgroup so far (arbitrary units)
       long long cur1 = -1, cur2 = -1, cur3 = -1;   // claimed, not yet enqueued
+      // The first summary item of a CTA is fixed (linear block index = CTA index) and enqueued before anything else: the
+      // first TMA loads of a launch do not wait for a ticket atomic and a readiness poll (two L2 round trips).  The
+      // ticket counter then hands out the items from `base1` on.
+      long long base1 = 0;
+#if MHLA_STATIC_FIRST
+      if (has1 && np2 == 0) {
+        base1 = n1tot < (long long)gridDim.x ? n1tot : (long long)gridDim.x;
+        if ((long long)blockIdx.x < base1) {
+          wg_load[pub & 1] += p.normalize ? 7 : 3;
+          emit(1, (int)(blockIdx.x / p.M), (int)(blockIdx.x % p.M));
+        }
+      }
+#endif
       while (true) {
         {  // claim what is missing; the atomics are independent and overlap
           const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0 && !(dedicated && (has2 || cur2 >= 0));
@@ -741,6 +772,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           if (n2) a2 = atomicAdd(tickets + 8, 1ull);
           if (n3) a3 = atomicAdd(tickets + 16, 1ull);
           if (n1) {
+            a1 += (unsigned long long)base1;
             if ((long long)a1 < n1tot) cur1 = (long long)a1;
             else {
               has1 = false;
@@ -924,18 +956,41 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         }
       }
     };
-    // same with the fused post-ops (POST instantiations only): optional per-column weight, SiLU gate and additive term
-    // read from the token row's own 128-byte pieces of the gate / add tensors; 32 columns at a time (register budget)
-    auto load_pack64_post = [&](uint32_t taddr, float scale, const float* wcol, const uint16_t* grow, const uint16_t* arow,
-                                uint32_t* pk) {
+    // same with the fused post-ops (POST instantiations only): optional per-column weight, SiLU gate and additive term.
+    // An epilogue thread owns one token ROW (its TMEM lane), but a warp instruction in which every lane reads 16 bytes of
+    // its own row touches 32 cache lines: measured, the L1 tag stage made the fused epilogue slower than separate
+    // elementwise passes (275 vs 262 us on the Wan layer).  So the warp fetches the gate / add pieces of ITS 32 rows
+    // coalesced - 8 lanes cover one row's [gate 64 B | add 64 B] of a 32-column half, 4 rows per instruction - bounces
+    // them through the (still free) rows of the staging slot the output tile is about to be written to, and every lane
+    // reads its own row back from shared memory.  32 columns at a time (register budget).
+    //   gbase / abase: gate / add tensors at this item's (b, h[, block]); ts_mine: this thread's token row (-1: none)
+    auto load_pack64_post = [&](uint32_t taddr, float scale, const float* wcol, const uint16_t* gbase, long long g_sw,
+                                const uint16_t* abase, long long a_sw, int ts_mine, int coff, uint8_t* buf, uint32_t* pk) {
+      const int pc = lane & 7, rsel = lane >> 3;
+      const uint16_t* const tb = pc < 4 ? gbase : abase;
+      const long long tsw = pc < 4 ? g_sw : a_sw;
+      const int row0 = et & ~31;   // first row of this warp inside the tile
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
+        uint4 tmp[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int ts = __shfl_sync(0xffffffffu, ts_mine, i * 4 + rsel);
+          tmp[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (tb != nullptr && ts >= 0) tmp[i] = __ldg(reinterpret_cast<const uint4*>(tb + (long long)ts * tsw + coff + hh * 32 + (pc & 3) * 8));
+        }
+        __syncwarp();   // the previous half's own-row reads are done
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = row0 + i * 4 + rsel;
+          *reinterpret_cast<uint4*>(buf + rr * 128 + ((pc ^ (rr & 7)) << 4)) = tmp[i];
+        }
+        __syncwarp();
         uint32_t gw[16], aw[16];
+        const uint4* rowp = reinterpret_cast<const uint4*>(buf + et * 128);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          uint4 g4 = make_uint4(0u, 0u, 0u, 0u), a4 = make_uint4(0u, 0u, 0u, 0u);
-          if (grow != nullptr) g4 = __ldg(reinterpret_cast<const uint4*>(grow + hh * 32) + i);
-          if (arow != nullptr) a4 = __ldg(reinterpret_cast<const uint4*>(arow + hh * 32) + i);
+          const uint4 g4 = rowp[i ^ (et & 7)], a4 = rowp[(4 + i) ^ (et & 7)];
           gw[4 * i] = g4.x; gw[4 * i + 1] = g4.y; gw[4 * i + 2] = g4.z; gw[4 * i + 3] = g4.w;
           aw[4 * i] = a4.x; aw[4 * i + 1] = a4.y; aw[4 * i + 2] = a4.z; aw[4 * i + 3] = a4.w;
         }
@@ -953,7 +1008,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             g2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gw[e]));
             a2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&aw[e]));
           }
-          if (grow != nullptr) {   // SiLU(g) = g / (1 + exp(-g))
+          if (gbase != nullptr) {   // SiLU(g) = g / (1 + exp(-g))
             x0 *= __fdividef(g2.x, 1.0f + __expf(-g2.x));
             x1 *= __fdividef(g2.y, 1.0f + __expf(-g2.y));
           }
@@ -962,6 +1017,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           else pk[hh * 16 + e] = pack_bf16x2(x0, x1);
         }
       }
+      __syncwarp();   // every lane has read its row: the rows may now be overwritten with the output tile
     };
     // x = hi + lo with hi, lo in the 16-bit I/O type
     auto split16 = [&](float x, uint16_t& hi, uint16_t& lo) {
@@ -994,6 +1050,17 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       return acc_n;
     };
 
+    // wait for the accumulator of the current item.  MHLA_EPI_POLL1: only the first warp of the warpgroup polls the
+    // mbarrier, the other three sleep in a named barrier (their polling loops would share issue slots with the other
+    // warpgroup's epilogue)
+    auto wait_tfull = [&](uint32_t ab_, uint32_t aphase_) {
+#if MHLA_EPI_POLL1
+      if (q4 == 0) mbar_wait_prof(&tfull[ab_], aphase_, prof_on, w_tfull);
+      named_bar_sync(bar_base + 2, kEpiThreads);
+#else
+      mbar_wait_prof(&tfull[ab_], aphase_, prof_on, w_tfull);
+#endif
+    };
     if (p.self_prep) {
       // No prologue kernel: the 256 epilogue threads of every CTA split their share of the fp32 mixing matrix into the
       // hi | lo planes the P2 items load by TMA (rows blockIdx.x, blockIdx.x + gridDim.x, ...) and announce it; the
@@ -1044,7 +1111,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const long long t_item = prof_on ? clock64() : 0;
       if (et == 0) trace_ev(p, 2, nitem, 0);
       if (it.type == 1) {
-        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        wait_tfull(ab, aphase);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         // rows of S live in TMEM lanes: D == 128 -> lane = row; D == 64 (M=64 MMA) -> row r in lane 32*(r/16)+r%16
@@ -1054,11 +1121,31 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         const size_t blk = (size_t)it.g * p.M + it.t;
         uint16_t* const srow = p.ws_S + blk * p.ncols;
         r.advance(p.nsub * kvs);
+#if MHLA_EARLY_P1
+        // D = 64: the whole accumulator (64 S columns + ksum) fits the register budget, so it is read FIRST and handed
+        // back to the issuer before the n_loc dot products and the staging of S - the MMAs of the item after next no
+        // longer wait for this epilogue
+        uint32_t pk_early[32];
+        uint32_t ks_early = 0;
+        if constexpr (D == 64) {
+          if (p.normalize) tmem_ld_x1(acc + kKsumCol, ks_early);
+          load_pack64(acc, 1.0f, pk_early);   // (its tcgen05.wait::ld covers the ksum column as well)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[ab]);
+        }
+#endif
         if (p.normalize) {
           // ---- n_loc first: it frees the Q stage(s) of the ring early
           uint32_t ks;
-          tmem_ld_x1(acc + kKsumCol, ks);
-          tmem_ld_wait();
+#if MHLA_EARLY_P1
+          if constexpr (D == 64) ks = ks_early;
+          else
+#endif
+          {
+            tmem_ld_x1(acc + kKsumCol, ks);
+            tmem_ld_wait();
+          }
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
           named_bar_sync(bar_base + 2, kEpiThreads);  // ksum_s complete
           uint16_t* const nbuf = srow + D * D;        // [hi: wpad][lo: wpad]
@@ -1092,22 +1179,31 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
           }
         }
-        for (int c = 0; c < D / 64; ++c) {
-          uint32_t pk[32];
-          load_pack64(acc + c * 64, 1.0f, pk);
+#if MHLA_EARLY_P1
+        if constexpr (D == 64) {
           uint8_t* buf = slot_acquire();
-          if (row_ok) stage_row(buf, row, pk);
-          chunk_copy(buf, reinterpret_cast<uint8_t*>(srow) + c * 128, (size_t)D * 2, D, D);
+          if (row_ok) stage_row(buf, row, pk_early);
+          chunk_copy(buf, reinterpret_cast<uint8_t*>(srow), (size_t)D * 2, D, D);
+        } else
+#endif
+        {
+          for (int c = 0; c < D / 64; ++c) {
+            uint32_t pk[32];
+            load_pack64(acc + c * 64, 1.0f, pk);
+            uint8_t* buf = slot_acquire();
+            if (row_ok) stage_row(buf, row, pk);
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(srow) + c * 128, (size_t)D * 2, D, D);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[ab]);
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[ab]);
         item_done();
       } else if (it.type == 2) {
         const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
         const int nvalid = p.M - ti * 128;       // rows of this tile inside the matrix (TMA used to clip them)
         const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
-        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        wait_tfull(ab, aphase);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         const float wsc = p.self_prep ? *wscale_s : __ldg(p.wscale);   // undo the power-of-two normalisation (exact)
@@ -1115,6 +1211,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           for (int c = 0; c < 4; ++c) {
             uint32_t pk[32];
             load_pack64(acc + c * 64, wsc, pk);
+#ifdef MHLA_EARLY_P2
+            if (c == 3) {   // last read of the accumulator: hand it back before the tile is staged and copied out
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[ab]);
+            }
+#endif
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
@@ -1134,9 +1237,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
                        (size_t)2 * p.wpad * 4, 128, nvalid);
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty[ab]);
+#ifdef MHLA_EARLY_P2
+        if (tc >= p.n2_scols)
+#endif
+        {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[ab]);
+        }
         r.advance((wres ? 1 : 2) * p.kslabs);
         item_done();
       } else {
@@ -1156,9 +1264,80 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             if (valid) dsum[sub] = __ldcg(dg + t) + __ldcg(dg + p.wpad + t) + p.eps;
           }
         }
-        mbar_wait_prof(&tfull[ab], aphase, prof_on, w_tfull);
+        // fused post-ops: this thread's token rows inside the gate / add tensors (-1: the row lies beyond the block and is
+        // never stored).  Formed BEFORE the wait for the accumulator, and the rows' 128-byte pieces are pulled into L2 now.
+        int ts_s[2] = {-1, -1};
+        const uint16_t* gbase = nullptr;
+        const uint16_t* abase = nullptr;
+        if constexpr (POST) {
+          if (p.post_gate != nullptr) gbase = p.post_gate + b * p.pg_sb + h * p.pg_sh + (G3D ? 0 : ib * p.pg_sm);
+          if (p.post_add != nullptr) abase = p.post_add + b * p.pa_sb + h * p.pa_sh + (G3D ? 0 : ib * p.pa_sm);
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            if (sub < p.nsub) {
+              if constexpr (!G3D) {   // block-major: token inside the block
+                const int t = sub * p.TW + et;
+                if (et < p.TW && t < p.w) ts_s[sub] = t;
+              } else {                // 3-D view: token inside the sample
+                if (et < p.g3_rows[sub]) {
+                  const int pp = p.g3_p2 * p.g3_p3, a = et / pp, rem = et - a * pp, y = rem / p.g3_p3, x = rem - y * p.g3_p3;
+                  const int wbi = ib % p.g3_wb, jj = ib / p.g3_wb, hbi = jj % p.g3_hb, fbi = jj / p.g3_hb;
+                  ts_s[sub] = ((fbi * p.g3_p1 + sub * p.g3_aper + a) * p.g3_H + hbi * p.g3_p2 + y) * p.g3_W + wbi * p.g3_p3 + x;
+                }
+              }
+              if (ts_s[sub] >= 0) {
+#pragma unroll
+                for (int c = 0; c < D / 64; ++c) {
+                  if (gbase != nullptr) prefetch_l2(gbase + (long long)ts_s[sub] * p.pg_sw + c * 64);
+                  if (abase != nullptr) prefetch_l2(abase + (long long)ts_s[sub] * p.pa_sw + c * 64);
+                }
+              }
+            }
+          }
+        }
+        wait_tfull(ab, aphase);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
+#if MHLA_EARLY_P3 == 1
+        // D = 64, no fused post-ops: both 64-column halves of the readout accumulator are scaled and rounded into
+        // registers first and the buffer goes back to the issuer BEFORE the two tiles are staged and stored
+        bool early_done = false;
+        if constexpr (D == 64 && !POST && !G3D) {
+          if (p.rms_w == nullptr) {
+            uint32_t pk0[32], pk1[32];
+            auto load_pack64_lr = [&](uint32_t taddr, float scale, uint32_t* pk) {   // 32 columns at a time: fewer live registers
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                tmem_ld_x32(taddr + hh * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                  const float a = __uint_as_float(v[2 * e]) * scale, bq = __uint_as_float(v[2 * e + 1]) * scale;
+                  if (p.is_fp16) { __half2 h0 = __floats2half2_rn(a, bq); pk[hh * 16 + e] = *reinterpret_cast<uint32_t*>(&h0); }
+                  else pk[hh * 16 + e] = pack_bf16x2(a, bq);
+                }
+              }
+            };
+            load_pack64_lr(acc, p.normalize ? 1.0f / dsum[0] : 1.0f, pk0);
+            if (p.nsub > 1) load_pack64_lr(acc + 128, p.normalize ? 1.0f / dsum[1] : 1.0f, pk1);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[ab]);
+            const uint64_t oh = p.o_hint ? kEvictFirst : kEvictNormal;
+            auto send = [&](int sub, const uint32_t* pk) {
+              uint8_t* buf = slot_acquire();
+              stage_row(buf, et, pk);
+              chunk_tma_begin();
+              if (et == 0) tma_store_5d_hint(&p.tmO, buf, 0, sub * p.TW, ib, h, b, oh);
+              chunk_tma_end();
+            };
+            send(0, pk0);
+            if (p.nsub > 1) send(1, pk1);
+            early_done = true;
+          }
+        }
+        if (!early_done) {
+#endif
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
           if (sub >= p.nsub) break;
@@ -1180,35 +1359,24 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
             rden *= rsqrtf(ss * (1.0f / D) + p.rms_eps);
           }
-          // fused post-ops: this thread's token row inside the gate / add tensors (rows beyond the block are never stored)
-          const uint16_t* grow = nullptr;
-          const uint16_t* arow = nullptr;
-          if constexpr (POST) {
-            bool rvalid;
-            long long tsel;   // block-major: token inside the block; 3-D view: token inside the sample
-            if constexpr (!G3D) {
-              const int t = sub * p.TW + et;
-              rvalid = et < p.TW && t < p.w;
-              tsel = t;
-            } else {
-              rvalid = et < p.g3_rows[sub];
-              const int pp = p.g3_p2 * p.g3_p3, a = et / pp, rem = et - a * pp, y = rem / p.g3_p3, x = rem - y * p.g3_p3;
-              const int wbi = ib % p.g3_wb, jj = ib / p.g3_wb, hbi = jj % p.g3_hb, fbi = jj / p.g3_hb;
-              tsel = ((long long)(fbi * p.g3_p1 + sub * p.g3_aper + a) * p.g3_H + hbi * p.g3_p2 + y) * p.g3_W + wbi * p.g3_p3 + x;
-            }
-            if (rvalid && p.post_gate != nullptr)
-              grow = p.post_gate + b * p.pg_sb + h * p.pg_sh + (G3D ? 0 : ib * p.pg_sm) + tsel * p.pg_sw;
-            if (rvalid && p.post_add != nullptr)
-              arow = p.post_add + b * p.pa_sb + h * p.pa_sh + (G3D ? 0 : ib * p.pa_sm) + tsel * p.pa_sw;
-          }
           for (int c = 0; c < D / 64; ++c) {
             uint32_t pk[32];
+            uint8_t* buf = nullptr;
             if constexpr (POST) {
-              load_pack64_post(acc + sub * 128 + c * 64, rden, p.rms_w != nullptr ? p.rms_w + c * 64 : nullptr,
-                               grow != nullptr ? grow + c * 64 : nullptr, arow != nullptr ? arow + c * 64 : nullptr, pk);
+              buf = slot_acquire();   // (the slot doubles as the bounce buffer of the gate / add pieces)
+              load_pack64_post(acc + sub * 128 + c * 64, rden, p.rms_w != nullptr ? p.rms_w + c * 64 : nullptr, gbase, p.pg_sw,
+                               abase, p.pa_sw, ts_s[sub], c * 64, buf, pk);
             } else if (p.rms_w != nullptr) load_pack64_w(acc + sub * 128 + c * 64, rden, p.rms_w + c * 64, pk);
             else load_pack64(acc + sub * 128 + c * 64, rden, pk);
-            uint8_t* buf = slot_acquire();
+#if MHLA_EARLY_P3 == 2
+            // last read of this accumulator buffer: hand it back to the issuer before the tile is staged and stored
+            if (sub == p.nsub - 1 && c == D / 64 - 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tempty[ab]);
+            }
+#endif
+            if constexpr (!POST) buf = slot_acquire();
             stage_row(buf, et, pk);
             chunk_tma_begin();
             // the output is never read again: mark its lines evict-first so that they leave L2 before the Q tiles the
@@ -1226,9 +1394,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             chunk_tma_end();
           }
         }
+#if MHLA_EARLY_P3 != 2
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tempty[ab]);
+#endif
+#if MHLA_EARLY_P3 == 1
+        }
+#endif
         r.advance(p3_stages<D>(p));
       }
       if (et == 0) trace_ev(p, 2, nitem, 2);

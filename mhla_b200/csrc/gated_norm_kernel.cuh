@@ -58,4 +58,39 @@ __global__ void __launch_bounds__(256) gated_norm_kernel(const GatedNormParams p
   }
 }
 
+// Post-ops of the Wan / DiT layers as ONE streaming pass behind the operator (mhla_utils.py:360-366, wan/model.py:1001-1003,
+// mhla.py:268-273):   out = x * silu(g) + add     (g == NULL: no gate, add == NULL: no additive term), fp32 math, one
+// rounding.  Rows of C elements (C % 8 == 0) with their own pitches; 16 bytes per thread and tensor, grid-stride.
+// (The same ops also exist INSIDE the readout epilogue - blockmix_kernel<D, G3D, true> - but an epilogue thread owns one
+// token row, and its dependent global loads queue behind the TMA stream of a saturated memory system: measured 283 us
+// fused vs 124 us + this pass on the Wan layer, profiles/r02c_notes.md.)
+struct GateAddParams {
+  const void* x; const void* g; const void* add; void* out;
+  long long rows, ld_x, ld_g, ld_a, ld_o;   // row pitches in elements
+  int C, fp16;
+};
+
+__global__ void __launch_bounds__(256) gate_add_kernel(const GateAddParams p) {
+  const int vec = p.C / 8;
+  const long long total = p.rows * vec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long row = idx / vec;
+    const int c = (int)(idx - row * vec) * 8;
+    float a[8], b[8];
+    aux_load8(p.x, row * p.ld_x + c, p.fp16, a);
+    if (p.g) {
+      aux_load8(p.g, row * p.ld_g + c, p.fp16, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] *= __fdividef(b[i], 1.0f + __expf(-b[i]));
+    }
+    if (p.add) {
+      aux_load8(p.add, row * p.ld_a + c, p.fp16, b);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += b[i];
+    }
+    aux_store8(p.out, row * p.ld_o + c, p.fp16, a);
+  }
+}
+
 }  // namespace mhla

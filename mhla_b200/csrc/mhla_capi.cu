@@ -689,6 +689,28 @@ int mhla_gated_rmsnorm(const mhla_gated_rmsnorm_desc* d, void* stream_) {
   return MHLA_OK;
 }
 
+int mhla_gate_add(const mhla_gate_add_desc* d, void* stream_) {
+  if (!d || !d->x || !d->out) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->rows < 1 || d->C < 8 || d->C % 8) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->g) |
+                       reinterpret_cast<uintptr_t>(d->add) | reinterpret_cast<uintptr_t>(d->out);
+  if ((al & 15) != 0 || d->ld_x % 8 || d->ld_out % 8 || (d->g && d->ld_g % 8) || (d->add && d->ld_add % 8) ||
+      d->ld_x < d->C || d->ld_out < d->C || (d->g && d->ld_g < d->C) || (d->add && d->ld_add < d->C))
+    return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::GateAddParams P{d->x, d->g, d->add, d->out, (long long)d->rows, (long long)d->ld_x, (long long)d->ld_g,
+                        (long long)d->ld_add, (long long)d->ld_out, d->C, d->dtype == MHLA_FP16};
+  const long long want = (d->rows * (d->C / 8) + 255) / 256, cap = (long long)dst->sms * 8;
+  const int grid = (int)(want < cap ? want : cap);
+  mhla::gate_add_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "gate_add_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
 int mhla_bwd_prep(const mhla_bwd_prep_desc* d, void* stream_) {
   if (!d || !d->dout || !d->out || !d->den || !d->dnum || !d->dden) return MHLA_ERR_INVALID_ARGUMENT;
   if (d->rows < 1 || (d->D != 64 && d->D != 128)) return MHLA_ERR_UNSUPPORTED_SHAPE;

@@ -203,6 +203,10 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const void* tmap, uint64
       "l"(hint)
       : "memory");
 }
+// L2 prefetch of the cache line holding `ptr` (generic address of global memory)
+__device__ __forceinline__ void prefetch_l2(const void* ptr) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+}
 // L2 prefetch of a tensor tile (no shared-memory destination, no completion tracking)
 __device__ __forceinline__ void tma_prefetch_5d(const void* tmap, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(

@@ -16,7 +16,7 @@ from einops import rearrange
 from torch import nn
 
 from ..mixing import BlockDistanceConv3D
-from ..ops import mhla_blockmix, mhla_blockmix_grid, wan_prep
+from ..ops import gate_add, mhla_blockmix, mhla_blockmix_grid, wan_prep
 
 
 class WanRMSNorm(nn.Module):
@@ -111,7 +111,11 @@ class _MHLAVideoBase(nn.Module):
         self.is_gated = gated
         self.fuse_out_norm = kwargs.get("fuse_out_norm", True)   # extension: per-head g_norm inside the kernel epilogue
         self.fast_path = kwargs.get("fast_path", True)           # extension: fused pre-processing + 3-D block TMA view
-        self.fuse_post = kwargs.get("fuse_post", True)           # extension: SiLU gate and "+ lepe" in the kernel epilogue
+        # extension: SiLU gate and "+ lepe" behind the operator.  True / "stream": ONE streaming launch (ops.gate_add) instead
+        # of three eager elementwise passes; "epilogue": inside the operator's readout epilogue (ABI v4 out_gate / out_add;
+        # measured slower than the streaming pass on a B200 - the epilogue's row-wise global loads queue behind the TMA
+        # stream, profiles/r02c_notes.md); False: plain torch ops
+        self.fuse_post = kwargs.get("fuse_post", True)
         self.is_lepe = lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
@@ -170,7 +174,7 @@ class _MHLAVideoBase(nn.Module):
         # the SiLU gate and "+ lepe" ride in the same epilogue (out = g_norm(o) * silu(g(x)) + lepe in fp32, one rounding:
         # mhla_utils.py:357-364, wan/model.py:1001-1003) whenever nothing un-fused sits between the operator and them
         post = {}
-        if self.fuse_post and ((self._gnorm == "head" and fuse) or self._gnorm is None):
+        if self.fuse_post == "epilogue" and ((self._gnorm == "head" and fuse) or self._gnorm is None):
             if self.is_gated:
                 post["out_gate"] = self.g(x).view(B, N, nh, D)
             if self.is_lepe:
@@ -188,10 +192,17 @@ class _MHLAVideoBase(nn.Module):
         out = out.reshape(B, N, C)
         if self._gnorm == "dim":
             out = self.g_norm(out)
-        if self.is_gated and "out_gate" not in post:
-            out = out * self.g_fn(self.g(x))
-        if self.is_lepe and "out_add" not in post:
-            out = out + lepe
+        need_gate, need_add = self.is_gated and "out_gate" not in post, self.is_lepe and "out_add" not in post
+        if (need_gate or need_add) and self.fuse_post and out.dtype in (torch.bfloat16, torch.float16) and C % 8 == 0:
+            gate = self.g(x) if need_gate else None
+            if gate is not None and gate.dtype != out.dtype:
+                gate = gate.to(out.dtype)
+            out = gate_add(out.contiguous(), gate, lepe if need_add else None)     # one launch: out * silu(g(x)) + lepe
+        else:
+            if need_gate:
+                out = out * self.g_fn(self.g(x))
+            if need_add:
+                out = out + lepe
         out = self.o(out)
         return self.out_rmsnorm(out) if self._out_norm else out
 

@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "gated_rmsnorm", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "gated_rmsnorm", "gate_add", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -449,6 +449,44 @@ def gated_rmsnorm(x: torch.Tensor, g: Optional[torch.Tensor], weight: Optional[t
     d.weight, d.eps, d.out = (wf.data_ptr() if wf is not None else None), float(eps), out.data_ptr()
     with torch.cuda.device(x.device):
         _capi.check(_capi.lib().mhla_gated_rmsnorm(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_gated_rmsnorm")
+    return out
+
+
+def gate_add(x: torch.Tensor, gate: Optional[torch.Tensor] = None, add: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = x * silu(gate) + add in one streaming launch (``mhla_gate_add``, csrc/gated_norm_kernel.cuh): the SiLU gate
+    and "+ lepe" that follow the operator in the Wan / DiT layers (mhla_utils.py:360-366, wan/model.py:1001-1003,
+    mhla.py:268-273).  x, gate, add: [..., C] bf16 / fp16 CUDA tensors of one shape (C % 8 == 0); ``out`` may be ``x``
+    (in place).  Inference only."""
+    _require_cuda(x, gate, add)
+    if x.dtype not in _DT or x.shape[-1] % 8:
+        raise ValueError("gate_add needs a bf16 / fp16 tensor whose last dim is a multiple of 8")
+    Cc = x.shape[-1]
+
+    def rows(t):   # [rows, C] with one row pitch; anything else is made contiguous first
+        t = t.detach()
+        if t.dtype != x.dtype:
+            t = t.to(x.dtype)
+        if tuple(t.shape) != tuple(x.shape):
+            raise ValueError("gate_add: gate / add must have the shape of x")
+        if not t.is_contiguous():
+            t = t.contiguous()
+        return t.view(-1, Cc)
+    x2 = rows(x)
+    g2 = rows(gate) if gate is not None else None
+    a2 = rows(add) if add is not None else None
+    if out is None:
+        out = torch.empty(tuple(x.shape), dtype=x.dtype, device=x.device)
+    elif out.dtype != x.dtype or tuple(out.shape) != tuple(x.shape) or not out.is_contiguous():
+        raise ValueError("gate_add: out must be a contiguous tensor of x's shape and dtype")
+    d = _capi.GateAddDesc()
+    d.rows, d.C, d.dtype = x2.shape[0], Cc, _DT[x.dtype]
+    d.x, d.ld_x = x2.data_ptr(), x2.stride(0)
+    d.g, d.ld_g = (g2.data_ptr(), g2.stride(0)) if g2 is not None else (None, 0)
+    d.add, d.ld_add = (a2.data_ptr(), a2.stride(0)) if a2 is not None else (None, 0)
+    d.out, d.ld_out = out.data_ptr(), Cc
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().mhla_gate_add(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_gate_add")
     return out
 
 

@@ -217,9 +217,35 @@ def test_wan_prep_kernel_matches_reference_preprocessing(in_dtype, plain):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("normalize_out,gated,lepe", [(False, False, False), (True, True, False), (True, False, True),
-                                                      (False, True, True)])
-def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated, lepe):
+@pytest.mark.parametrize("dtype,gated,added", [(torch.bfloat16, True, True), (torch.float16, True, False),
+                                               (torch.bfloat16, False, True)])
+def test_gate_add_kernel(dtype, gated, added):
+    """csrc/gated_norm_kernel.cuh gate_add_kernel (mhla_gate_add): out = x * silu(g) + add, fp32 math, one rounding -
+    the post-ops of mhla_utils.py:360-366 / wan/model.py:1001-1003 as one streaming launch; also in place."""
+    import mhla_b200
+    g_ = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 333, 12, 128, generator=g_).to(dtype)
+    gt = torch.randn(2, 333, 12, 128, generator=g_).to(dtype) if gated else None
+    ad = torch.randn(2, 333, 12, 128, generator=g_).to(dtype) if added else None
+    ref = x.float()
+    if gated:
+        ref = ref * torch.nn.functional.silu(gt.float())
+    if added:
+        ref = ref + ad.float()
+    xd = x.cuda()
+    y = mhla_b200.gate_add(xd, None if gt is None else gt.cuda(), None if ad is None else ad.cuda())
+    tol = 3e-3 if dtype == torch.bfloat16 else 5e-4
+    assert oracle.err_ratio(ref, y.float().cpu()) < tol
+    y2 = mhla_b200.gate_add(xd, None if gt is None else gt.cuda(), None if ad is None else ad.cuda(), out=xd)   # in place
+    assert y2.data_ptr() == xd.data_ptr() and torch.equal(y2, y)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("normalize_out,gated,lepe,post", [(False, False, False, True), (True, True, False, True),
+                                                           (True, False, True, True), (False, True, True, True),
+                                                           (False, True, True, "epilogue"), (True, True, False, "epilogue"),
+                                                           (False, True, True, False)])
+def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated, lepe, post):
     """MHLA_Video_Uni at Wan's block shape (7*6*5 = 210 tokens per block, D = 128): the fused inference path (one
     pre-processing launch + the 3-D block view) against the module's own reference-style path (torch pre-processing +
     block-major rearrange copies), bf16 autocast as in the reference's sampler (inference.py:284)."""
@@ -227,7 +253,7 @@ def test_wan_module_fused_path_equals_reference_style_path(normalize_out, gated,
     dim, heads, layout, grid = 256, 2, (1, 2, 2), (7, 12, 10)
     N = grid[0] * grid[1] * grid[2]
     m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=normalize_out, is_gated=gated,
-                       is_lepe=lepe).cuda().eval()
+                       is_lepe=lepe, fuse_post=post).cuda().eval()   # post-ops: streaming launch / readout epilogue / torch
     m.block_attn.conv.weight.data.mul_(1.0 + 0.1 * torch.rand_like(m.block_attn.conv.weight))
     x = torch.randn(2, N, dim, device="cuda")
     gs = torch.tensor([list(grid)] * 2, dtype=torch.long)

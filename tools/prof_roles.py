@@ -46,3 +46,13 @@ tot = p[:, 2].mean()
 for i, n in enumerate(names):
     col = p[:, i]
     print(f"{n:18s} mean {col.mean():12.0f}  min {col.min():12.0f}  max {col.max():12.0f}   ({100 * col.mean() / tot:5.1f}% of producer lifetime)")
+if "--per-cta" in sys.argv:
+    # one row per CTA, sorted by the number of items its warpgroup 0 handled (the dynamic tickets give faster SMs more)
+    order = sorted(range(148), key=lambda c: float(p[c, 11]))
+    print("cta items(wg0) prod.wait_empty prod.wait_dep mma.wait_full mma.wait_tempty epi.wait_tfull  (cycles)")
+    for c in order:
+        print(f"{c:3d} {int(p[c, 11]):3d} {int(p[c, 0]):8d} {int(p[c, 1]):8d} {int(p[c, 3]):8d} {int(p[c, 4]):8d} {int(p[c, 5]):8d}")
+    slow, fast = order[0], order[-1]
+    print(f"slowest CTA {slow}, fastest CTA {fast}")
+    with open(os.path.join(ROOT, "gpurun_out", "slow_fast_cta.txt"), "w") as f:
+        f.write(f"{slow} {fast}\n")

@@ -12,6 +12,8 @@ from mhla_b200 import _capi  # noqa: E402
 
 normalize = "--no-normalize" not in sys.argv
 tag = "norm" if normalize else "nonorm"
+if os.environ.get("MHLA_TRACE_CTA"):
+    tag += "_cta" + os.environ["MHLA_TRACE_CTA"]
 kw = {}
 if "--p1only" in sys.argv:
     kw = dict(debug_flags=_capi.FLAG_STOP_AFTER_P1)

@@ -65,13 +65,13 @@ m = MHLA_Video_Uni(dim, heads, None, 0.0, None, True, layout, normalize_out=Fals
 x = torch.randn(1, N, dim, device="cuda")
 gs, sl = torch.tensor([list(grid)], dtype=torch.long), torch.tensor([N])
 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-    m.fuse_post = True
+    m.fuse_post = True          # (streaming gate_add launch behind the operator)
     t_f = timed(lambda: m(x, sl, gs, freqs))
     y1 = m(x, sl, gs, freqs)
     m.fuse_post = False
     t_u = timed(lambda: m(x, sl, gs, freqs))
     y2 = m(x, sl, gs, freqs)
-print(f"B=1 gated + lepe layer: epilogue-fused gate/lepe {t_f:.0f} us vs separate passes {t_u:.0f} us, rel diff "
+print(f"B=1 gated + lepe layer: one gate_add launch {t_f:.0f} us vs torch elementwise passes {t_u:.0f} us, rel diff "
       f"{float((y1.float() - y2.float()).norm() / y2.float().norm()):.2e}")
 
 # training step (forward + backward of the whole layer, bf16 autocast) in the shipped configuration: 3-D block view with
@@ -91,3 +91,21 @@ t_g = timed(train_step, reps=5)
 m.fast_path = False
 t_b = timed(train_step, reps=5)
 print(f"B=1 training step of the layer: 3-D block view {t_g:.0f} us vs block-major copies {t_b:.0f} us")
+
+# the fused gate / "+ lepe" epilogue at OPERATOR level (the layer numbers above are dominated by the depthwise Conv3d):
+# one launch with out_gate / out_add against the plain launch followed by the eager elementwise passes
+q = torch.randn(1, N, heads, dim // heads, device="cuda").bfloat16()
+gt = torch.randn(1, N, heads, dim // heads, device="cuda").bfloat16()
+ad = torch.randn(1, N, heads, dim // heads, device="cuda").bfloat16()
+W = m.block_attn.conv.weight.detach()
+with torch.no_grad():
+    t_plain = timed(lambda: mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False), reps=20)
+    t_fused = timed(lambda: mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False, out_gate=gt, out_add=ad), reps=20)
+    t_sep = timed(lambda: mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False) * torch.nn.functional.silu(gt) + ad, reps=20)
+
+    def streamed():
+        o = mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False)
+        return mhla_b200.gate_add(o, gt, ad, out=o)
+    t_stream = timed(streamed, reps=20)
+print(f"operator, Wan B=1: plain {t_plain:.0f} us, gate + add fused in the epilogue {t_fused:.0f} us, plain + eager silu/mul/add "
+      f"{t_sep:.0f} us, plain + ONE streaming gate_add launch {t_stream:.0f} us")
