@@ -44,7 +44,7 @@ def measured_peaks():
 
 def measured_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), or None."""
-    for name in ("r02_traffic.json", "r01_traffic.json"):
+    for name in ("r02c_traffic.json", "r02_traffic.json", "r01_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 return float(json.load(f)["dram_bytes_per_launch"]), name
@@ -270,6 +270,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="ranges of (b,h) units the host entry point pipelines over")
     ap.add_argument("--three-launch", action="store_true", help="three PDL-chained phase launches instead of the fused kernel")
     args = ap.parse_args()
 
@@ -392,7 +393,7 @@ def main():
     def e2e_step():
         # the public host-tensor entry point: pinned H2D of q,k,v, the kernel and the D2H of the output, pipelined over
         # ranges of (b,h) units on three streams (mhla_b200.ops.mhla_host)
-        mhla_b200.mhla_host(h5(hq), h5(hk), h5(hv), W, out=h5(hout), normalize=normalize, chunks=min(8, nloc))
+        mhla_b200.mhla_host(h5(hq), h5(hk), h5(hv), W, out=h5(hout), normalize=normalize, chunks=min(args.e2e_chunks, nloc))
 
     e2e_step()
     torch.cuda.synchronize()
