@@ -14,7 +14,7 @@ from einops import rearrange
 from torch import nn
 
 from ..mixing import BlockDistanceConv
-from ..ops import mhla_blockmix
+from ..ops import gate_add, mhla_blockmix
 
 
 class _MHLAImage(nn.Module):
@@ -96,12 +96,19 @@ class _MHLAImage(nn.Module):
             # inference: the kernel writes straight into the "(b h) n w d -> b n w (h d)" layout (no head-merge copy)
             cdtype = q.dtype if q.dtype in (torch.bfloat16, torch.float16) else torch.bfloat16
             obuf = torch.empty((B, M, w, H, D), dtype=cdtype, device=x.device)
-            # "+ lepe" (mhla.py:271-273) rides in the readout epilogue: added in fp32 before the single rounding
-            add = lepe.reshape(B, M, w, H, D).permute(0, 3, 1, 2, 4) if self.fuse_lepe else None
+            # "+ lepe" (mhla.py:271-273): short sequences (the whole unit on chip, csrc/smalln_kernel.cuh) add it in the
+            # readout epilogue, in fp32 before the single rounding; above that size the general kernel's epilogue has no
+            # latency budget for a second input stream and ONE streaming launch behind the operator adds it
+            small = D == 64 and M <= 64 and M * w <= 256
+            add = lepe.reshape(B, M, w, H, D).permute(0, 3, 1, 2, 4) if (self.fuse_lepe and small) else None
             mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True, out=obuf.permute(0, 3, 1, 2, 4), out_add=add)   # mhla.py:262-268
-            out = obuf.view(B, M, w, H * D).to(x.dtype)
-            if add is None:
-                out = out + lepe
+            out = obuf.view(B, M, w, H * D)
+            if add is None and self.fuse_lepe and lepe.dtype == cdtype and (H * D) % 8 == 0:
+                out = gate_add(out, None, lepe, out=out).to(x.dtype)
+            elif add is None:
+                out = out.to(x.dtype) + lepe
+            else:
+                out = out.to(x.dtype)
             out = self.to_out(out)
             return out.view(B, M * w, -1) if squeeze else out
         else:

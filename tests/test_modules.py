@@ -143,6 +143,23 @@ def test_dit_module_padded_head_dim_and_fp16_autocast():
 
 
 @pytest.mark.gpu
+def test_dit_module_lepe_paths_agree_above_the_short_sequence_size():
+    """MHLA4DiT at N = 1024 tokens (16 blocks of 64; the general kernel) under bf16 autocast: "+ lepe" as one streaming
+    launch behind the operator (default) against the plain torch add, and at N = 256 (short-sequence kernel: lepe added in
+    the readout epilogue) against the same."""
+    torch.manual_seed(1)
+    for embed_len, bs in ((1024, 64), (256, 16)):
+        m = MHLA4DiT(128, heads=2, dropout=0.0, block_size=bs, embed_len=embed_len, qkv_bias=True).eval().cuda()
+        x = torch.randn(2, embed_len // bs, bs, 128, device="cuda")
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            m.fuse_lepe = True
+            y1 = m(x)
+            m.fuse_lepe = False
+            y2 = m(x)
+        assert oracle.err_ratio(y2.float().cpu(), y1.float().cpu()) < 8e-3
+
+
+@pytest.mark.gpu
 def test_modules_train_through_the_operator():
     """loss.backward() reaches the projections AND the trainable mixing matrix (the reference trainers clamp
     piece_attn.conv.weight after every step, mhla_dit/train.py:308-310); gradients match the oracle's autograd."""
