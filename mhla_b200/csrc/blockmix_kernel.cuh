@@ -33,11 +33,19 @@
 #ifndef MHLA_EARLY_P3
 #define MHLA_EARLY_P3 2
 #endif
+// 1: the first summary item of every CTA is fixed (no ticket round trip before the first loads); 2: only for D = 128
+// (measured: Wan layer 119.3 -> 117.7 us, headline 141.0 -> 141.6 us, profiles/r02c_ab_2.log)
 #ifndef MHLA_STATIC_FIRST
-#define MHLA_STATIC_FIRST 0
+#define MHLA_STATIC_FIRST 2
 #endif
 #ifndef MHLA_EPI_POLL1
 #define MHLA_EPI_POLL1 0
+#endif
+// D = 64 instantiations: FOUR accumulator buffers of 128 TMEM columns instead of two of 256 (a P1 item needs 64 + 16
+// columns, a readout item 2 x 64), so the tcgen05 issuer may run up to four items ahead of the epilogues; mixing items
+// then cover 128 instead of 256 columns of [S | n_loc] (the host's tile grid is refined inside the kernel).
+#ifndef MHLA_ACC4
+#define MHLA_ACC4 0
 #endif
 
 namespace mhla {
@@ -288,8 +296,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmemBars);
   uint64_t* empty = full + kMaxStages;
   uint64_t* tfull = empty + kMaxStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* tempty = tfull + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 4);
   uint32_t* q_published = tmem_slot + 1;   // items the scheduler warp (warp 2) has enqueued
   uint32_t* q_started = tmem_slot + 2;     // items the producer has picked up (throttles the scheduler's run-ahead)
   uint32_t* wg_done = tmem_slot + 3;       // [2]: workspace-producing items finished by each epilogue warpgroup
@@ -307,10 +315,16 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
   // while the mode-4 grid is still draining (no griddepcontrol.wait: the counters carry the dependency)
   const bool dynamic = p.mode == 0 || p.mode == 4 || p.mode == 5;
   const bool wres = dynamic && (int)blockIdx.x < p.np2 && p.n2_rows == 1 && p.kslabs <= 2;
+  // accumulator buffers (see MHLA_ACC4): number, width, column of ksum inside a P1 buffer, column stride between the two
+  // sub-tiles of a readout item, width of a mixing item and the mixing tile grid that follows from it
+  constexpr bool kAcc4 = (D == 64) && (MHLA_ACC4 != 0);
+  constexpr uint32_t kNB = kAcc4 ? 4 : 2, kACols = kAcc4 ? 128 : kAccCols, kKsC = kAcc4 ? 64 : kKsumCol, kSubC = kAcc4 ? 64 : 128;
+  constexpr int kPN = kAcc4 ? 128 : 256;
+  const int n2_cols = p.n2_cols * (256 / kPN), n2_scols = p.n2_scols * (256 / kPN);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kMaxStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&tfull[i], 2); mbar_init(&tempty[i], 4);   // tfull: tcgen05.commit + the issuer's own arrive (see below)
     }
     fence_barrier_init();
@@ -456,14 +470,14 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           prefetch_block((long long)it.g * p.M + it.t, true, p.normalize != 0, false);
         } else if (it.type == 2) {
           if (dynamic) wait_dependency();
-          const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+          const int ti = it.t / n2_cols, tc = it.t % n2_cols;
           for (int slab = 0; slab < p.kslabs; ++slab) {
             // stage X: mix hi | mix lo, [128 i][64 j] each; stage Y: [64 j][256 cols] as 4 tiles of 64 columns
             uint8_t* st;
             if (!wres) {
               mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
               st = ring + r.idx() * kStageBytes;
-              const bool need_lo = !(p.is_fp16 || p.mix_hi_only) || tc >= p.n2_scols;
+              const bool need_lo = !(p.is_fp16 || p.mix_hi_only) || tc >= n2_scols;
               mbar_arrive_expect_tx(&full[r.idx()], need_lo ? 32768 : 16384);
               tma_load_3d(st, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 0, kEvictLast);
               if (need_lo) tma_load_3d(st + 16384, &p.tmW, &full[r.idx()], slab * 64, ti * 128, 1, kEvictLast);
@@ -471,9 +485,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             }
             mbar_wait_prof(&empty[r.idx()], r.phase ^ 1, prof_on, w_empty);
             st = ring + r.idx() * kStageBytes;
-            mbar_arrive_expect_tx(&full[r.idx()], 32768);
-            for (int n4 = 0; n4 < 4; ++n4)
-              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.idx()], tc * 256 + n4 * 64, slab * 64, it.g, kEvictNormal);
+            mbar_arrive_expect_tx(&full[r.idx()], (kPN / 64) * 8192);
+            for (int n4 = 0; n4 < kPN / 64; ++n4)
+              tma_load_3d(st + n4 * 8192, &p.tmSld, &full[r.idx()], tc * kPN + n4 * 64, slab * 64, it.g, kEvictNormal);
             r.advance();
           }
         } else {
@@ -533,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint64_t desc_ones = make_smem_desc(ones_addr, 256, 128, kSwizzleNone);
       const uint32_t idesc_p1 = make_idesc(fmt16, 1, 1, D, D);
       const uint32_t idesc_p1_ones = make_idesc(fmt16, 1, 1, D, 16);
-      const uint32_t idesc_p2 = make_idesc(fmt16, 0, 1, 128, 256);
+      const uint32_t idesc_p2 = make_idesc(fmt16, 0, 1, 128, kPN);
       const uint32_t idesc_p3 = make_idesc(fmt16, 0, 1, 128, D);
       // This lane's instruction stream is latency-bound (one thread, dependent integer ops), so the issue loops carry
       // as few instructions as possible: descriptors are built once per stage and advanced by adding to the 14-bit
@@ -543,8 +557,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       const uint64_t tmpl_k = make_smem_desc(0, 0, 1024, kSwizzle128);           // K-major
       auto dsc = [](uint64_t tmpl, uint32_t saddr) -> uint64_t { return tmpl | (uint64_t)((saddr & 0x3FFFF) >> 4); };
       while (sched.next(it)) {
-        const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
-        const uint32_t acc = tmem_base + ab * kAccCols;
+        const uint32_t ab = nitem & (kNB - 1), aphase = (nitem / kNB) & 1;
+        const uint32_t acc = tmem_base + ab * kACols;
         trace_ev(p, 1, nitem, 0);
         mbar_wait_prof(&tempty[ab], aphase ^ 1, prof_on, w_tempty);
         tc_fence_after();
@@ -580,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               for (int ks = 0; ks < 8; ++ks)
                 if (ks < ksteps) {
                   mma_f16_ss(acc, da0 + ks * 128, db0 + ks * 128, idesc_p1, ks ? 1u : first);
-                  mma_f16_ss(acc + kKsumCol, da0 + ks * 128, desc_ones, idesc_p1_ones, ks ? 1u : first);
+                  mma_f16_ss(acc + kKsC, da0 + ks * 128, desc_ones, idesc_p1_ones, ks ? 1u : first);
                 }
             } else {
 #pragma unroll
@@ -599,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #pragma unroll 1
               for (int ks = 0; ks < ksteps; ++ks) {
                 const uint64_t da = make_smem_desc(n_addr + ks * 2048, 16384, 1024, kSwizzle128);
-                mma_f16_ss(acc + kKsumCol, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
+                mma_f16_ss(acc + kKsC, da, desc_ones, idesc_p1_ones, (sub | ks) != 0);
               }
               mma_commit(&empty[r.idx()]);
               r.advance();
@@ -638,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             // fp16 I/O: the S columns take the "hi" plane only (11 significant bits on a power-of-two normalised matrix -
             // finer than the 16-bit S it multiplies); the normaliser columns, and everything in bf16 (8-bit planes;
             // tcgen05 kind::f16 does not take an f16 A with a bf16 B), add the "lo" plane.
-            if (!(p.is_fp16 || p.mix_hi_only) || (it.t % p.n2_cols) >= p.n2_scols) {
+            if (!(p.is_fp16 || p.mix_hi_only) || (it.t % n2_cols) >= n2_scols) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 mma_f16_ss(acc, dhi0 + ks * 2, db0 + ks * 128, idesc_p2, ks ? 1u : first);
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             const uint64_t da0 = dsc(tmpl_k, a_addr), db0 = dsc(tmpl_mn16k, b_addr);
 #pragma unroll
             for (int ks = 0; ks < D / 16; ++ks)   // K-major A: 4 k-steps (32 B each) per 64-channel tile, tiles 16 KB apart
-              mma_f16_ss(acc + sub * 128, da0 + (ks >> 2) * 1024 + (ks & 3) * 2, db0 + ks * 128, idesc_p3, ks != 0);
+              mma_f16_ss(acc + sub * kSubC, da0 + (ks >> 2) * 1024 + (ks & 3) * 2, db0 + ks * 128, idesc_p3, ks != 0);
             r.advance();
           }
           const int ns = p3_stages<D>(p);
@@ -701,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
     // belong to later groups than the P3 item that is being waited for.
     if (elect_one()) {
       const long long n1tot = (long long)p.G * p.M;
-      const int n2per = p.n2_rows * p.n2_cols;
+      const int n2per = p.n2_rows * n2_cols;
       const long long n2tot = (long long)p.G * n2per;
       const bool dyn = dynamic;
       // The block mixing of a group sits on the critical path between its summaries and its readout; with np2 > 0 a few
@@ -755,15 +769,13 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       // first TMA loads of a launch do not wait for a ticket atomic and a readiness poll (two L2 round trips).  The
       // ticket counter then hands out the items from `base1` on.
       long long base1 = 0;
-#if MHLA_STATIC_FIRST
-      if (has1 && np2 == 0) {
+      if ((MHLA_STATIC_FIRST == 1 || (MHLA_STATIC_FIRST == 2 && D == 128)) && has1 && np2 == 0) {
         base1 = n1tot < (long long)gridDim.x ? n1tot : (long long)gridDim.x;
         if ((long long)blockIdx.x < base1) {
           wg_load[pub & 1] += p.normalize ? 7 : 3;
           emit(1, (int)(blockIdx.x / p.M), (int)(blockIdx.x % p.M));
         }
       }
-#endif
       while (true) {
         {  // claim what is missing; the atomics are independent and overlap
           const bool n1 = has1 && cur1 < 0, n2 = has2 && cur2 < 0, n3 = has3 && cur3 < 0 && !(dedicated && (has2 || cur2 >= 0));
@@ -797,7 +809,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         // still in L2), except that the final `tail` groups - whose block mixing is still in flight when the readout
         // begins - come at the very end
         if (g3 >= 0 && p.mode == 0 && p.policy == 1 && p.reverse3) {
-          const int tail = p.G > 6 ? 3 : 0;
+          const int tail = p.G > 2 * p.reverse3 ? p.reverse3 : 0;
           if (g3 < p.G - tail) g3 = p.G - tail - 1 - g3;
         }
         {  // both polls are in flight together: one L2 round trip per decision
@@ -1101,9 +1113,9 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
       if (t256 == 0) red_release_gpu_add(p.counters + (size_t)2 * p.G * p.cnt_stride + 64, 1u);
     }
     while (sched.next_warp(it, lane)) {
-      const uint32_t ab = nitem & 1, aphase = (nitem >> 1) & 1;
-      const uint32_t acc = tmem_base + ab * kAccCols + lane_sel;
-      if ((int)ab != wg) {   // the other warpgroup's item: only keep the ring bookkeeping in step
+      const uint32_t ab = nitem & (kNB - 1), aphase = (nitem / kNB) & 1;
+      const uint32_t acc = tmem_base + ab * kACols + lane_sel;
+      if ((int)(ab & 1) != wg) {   // the other warpgroup's item: only keep the ring bookkeeping in step
         r.advance(it.type == 1 ? p1_stages<D>(p) : (it.type == 2 ? (wres ? 1 : 2) * p.kslabs : p3_stages<D>(p)));
         ++nitem;
         continue;
@@ -1128,7 +1140,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         uint32_t pk_early[32];
         uint32_t ks_early = 0;
         if constexpr (D == 64) {
-          if (p.normalize) tmem_ld_x1(acc + kKsumCol, ks_early);
+          if (p.normalize) tmem_ld_x1(acc + kKsC, ks_early);
           load_pack64(acc, 1.0f, pk_early);   // (its tcgen05.wait::ld covers the ksum column as well)
           tc_fence_before();
           __syncwarp();
@@ -1143,7 +1155,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           else
 #endif
           {
-            tmem_ld_x1(acc + kKsumCol, ks);
+            tmem_ld_x1(acc + kKsC, ks);
             tmem_ld_wait();
           }
           if (row_ok) ksum_s[row] = __uint_as_float(ks);
@@ -1200,19 +1212,19 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
         }
         item_done();
       } else if (it.type == 2) {
-        const int ti = it.t / p.n2_cols, tc = it.t % p.n2_cols;
+        const int ti = it.t / n2_cols, tc = it.t % n2_cols;
         const int nvalid = p.M - ti * 128;       // rows of this tile inside the matrix (TMA used to clip them)
         const size_t row0 = (size_t)it.g * p.M + (size_t)ti * 128;
         wait_tfull(ab, aphase);
         if (et == 0) trace_ev(p, 2, nitem, 1);
         tc_fence_after();
         const float wsc = p.self_prep ? *wscale_s : __ldg(p.wscale);   // undo the power-of-two normalisation (exact)
-        if (tc < p.n2_scols) {
-          for (int c = 0; c < 4; ++c) {
+        if (tc < n2_scols) {
+          for (int c = 0; c < kPN / 64; ++c) {
             uint32_t pk[32];
             load_pack64(acc + c * 64, wsc, pk);
 #ifdef MHLA_EARLY_P2
-            if (c == 3) {   // last read of the accumulator: hand it back before the tile is staged and copied out
+            if (c == kPN / 64 - 1) {   // last read of the accumulator: hand it back before the tile is staged and copied out
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -1220,12 +1232,12 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
 #endif
             uint8_t* buf = slot_acquire();
             stage_row(buf, et, pk);
-            chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * 256 + c * 64),
+            chunk_copy(buf, reinterpret_cast<uint8_t*>(p.ws_St + row0 * (size_t)(D * D) + tc * kPN + c * 64),
                        (size_t)D * D * 2, 128, nvalid);
           }
         } else {
-          for (int q = 0; q < 8; ++q) {
-            const int col0 = (tc - p.n2_scols) * 256 + q * 32;
+          for (int q = 0; q < kPN / 32; ++q) {
+            const int col0 = (tc - n2_scols) * kPN + q * 32;
             if (col0 >= 2 * p.wpad) break;   // uniform: nothing left in this tile
             tmem_ld_x32(acc + q * 32, v);
             tmem_ld_wait();
@@ -1238,7 +1250,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
           }
         }
 #ifdef MHLA_EARLY_P2
-        if (tc >= p.n2_scols)
+        if (tc >= n2_scols)
 #endif
         {
           tc_fence_before();
@@ -1319,7 +1331,7 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
               }
             };
             load_pack64_lr(acc, p.normalize ? 1.0f / dsum[0] : 1.0f, pk0);
-            if (p.nsub > 1) load_pack64_lr(acc + 128, p.normalize ? 1.0f / dsum[1] : 1.0f, pk1);
+            if (p.nsub > 1) load_pack64_lr(acc + kSubC, p.normalize ? 1.0f / dsum[1] : 1.0f, pk1);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[ab]);
@@ -1348,8 +1360,8 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             float ss = 0.f;
             for (int c = 0; c < D / 64; ++c) {
               uint32_t v2[32];
-              tmem_ld_x32(acc + sub * 128 + c * 64, v);
-              tmem_ld_x32(acc + sub * 128 + c * 64 + 32, v2);
+              tmem_ld_x32(acc + sub * kSubC + c * 64, v);
+              tmem_ld_x32(acc + sub * kSubC + c * 64 + 32, v2);
               tmem_ld_wait();
 #pragma unroll
               for (int e = 0; e < 32; ++e) {
@@ -1364,10 +1376,10 @@ __global__ void __launch_bounds__(kThreads, 1) blockmix_kernel(const __grid_cons
             uint8_t* buf = nullptr;
             if constexpr (POST) {
               buf = slot_acquire();   // (the slot doubles as the bounce buffer of the gate / add pieces)
-              load_pack64_post(acc + sub * 128 + c * 64, rden, p.rms_w != nullptr ? p.rms_w + c * 64 : nullptr, gbase, p.pg_sw,
+              load_pack64_post(acc + sub * kSubC + c * 64, rden, p.rms_w != nullptr ? p.rms_w + c * 64 : nullptr, gbase, p.pg_sw,
                                abase, p.pa_sw, ts_s[sub], c * 64, buf, pk);
-            } else if (p.rms_w != nullptr) load_pack64_w(acc + sub * 128 + c * 64, rden, p.rms_w + c * 64, pk);
-            else load_pack64(acc + sub * 128 + c * 64, rden, pk);
+            } else if (p.rms_w != nullptr) load_pack64_w(acc + sub * kSubC + c * 64, rden, p.rms_w + c * 64, pk);
+            else load_pack64(acc + sub * kSubC + c * 64, rden, pk);
 #if MHLA_EARLY_P3 == 2
             // last read of this accumulator buffer: hand it back to the issuer before the tile is staged and stored
             if (sub == p.nsub - 1 && c == D / 64 - 1) {

@@ -83,7 +83,7 @@ constexpr int kCntStride = 16;   // dependency counters sit 64 bytes apart (sepa
 
 // Tuning / debugging knobs of the blockmix kernel, read from the environment ONCE (first call).
 struct Knobs {
-  int run_ahead = 2, mix_hi_only = -1, o_hint = 1, q_hint = 1, trace_cta = 0, slots = 2;
+  int run_ahead = 2, mix_hi_only = -1, o_hint = 1, q_hint = 1, trace_cta = 0, slots = 2, reverse3 = 0;
   bool no_pack = false, no_self_prep = false;
 };
 const Knobs& knobs() {
@@ -99,6 +99,8 @@ const Knobs& knobs() {
     k.q_hint = geti("MHLA_QHINT", 1);
     k.trace_cta = geti("MHLA_TRACE_CTA", 0);
     k.slots = geti("MHLA_SLOTS", 2) == 1 ? 1 : 2;
+    k.reverse3 = geti("MHLA_REVERSE3", 0);   // n > 0: fused readout walks the groups backwards, the last n groups at the very end
+    if (k.reverse3 < 0) k.reverse3 = 0;
     k.no_pack = std::getenv("MHLA_NO_PACK") != nullptr;
     k.no_self_prep = std::getenv("MHLA_NO_SELF_PREP") != nullptr;
   });
@@ -504,7 +506,7 @@ int mhla_fwd_blockmix(const mhla_blockmix_desc* d, void* stream_) {
   P.mix_hi_only = kn.mix_hi_only >= 0 ? kn.mix_hi_only : ((d->D == 128 && d->dtype == MHLA_BF16) ? 1 : 0);
   P.o_hint = kn.o_hint;
   P.q_hint = kn.q_hint;
-  P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = 0;   // (round-1 tuning options, fixed at their best values)
+  P.window = 8; P.np2 = 0; P.policy = 1; P.pf_dist = 0; P.reverse3 = kn.reverse3;   // (round-1 tuning options, fixed at their best values)
   // fused gate / additive term: separate instantiations, so the plain kernels' code is untouched by them
   const bool post = d->out_gate.ptr != nullptr || d->out_add.ptr != nullptr;
   auto kern = pl.g3d ? (d->D == 64 ? mhla::blockmix_kernel<64, true> : mhla::blockmix_kernel<128, true>)

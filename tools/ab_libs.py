@@ -19,7 +19,14 @@ from mhla_b200 import _capi  # noqa: E402
 args = [a for a in sys.argv[1:] if "=" in a and not a.startswith("--")]
 reps = int(sys.argv[sys.argv.index("--reps") + 1]) if "--reps" in sys.argv else 3
 shape_sel = sys.argv[sys.argv.index("--shapes") + 1].split(",") if "--shapes" in sys.argv else ["headline", "nonorm", "wan"]
-libs = [(a.split("=", 1)[0], os.path.abspath(a.split("=", 1)[1])) for a in args]
+# name=path.so[@ENV=VAL[,ENV=VAL]]: the environment is set while the library makes its FIRST blockmix call (that is when it
+# reads its tuning knobs); the same build under two knob settings needs two copies of the file (one dlopen handle per path)
+libs, envs = [], {}
+for a in args:
+    name, rest = a.split("=", 1)
+    path, _, env = rest.partition("@")
+    libs.append((name, os.path.abspath(path)))
+    envs[name] = dict(kv.split("=", 1) for kv in env.split(",")) if env else {}
 SHAPES = {
     "headline": (2, 16, 128, 256, 64, True, False),
     "nonorm": (2, 16, 128, 256, 64, False, False),
@@ -59,6 +66,12 @@ def timed(fn, n=40):
 handles = {}
 for name, path in libs:
     handles[name] = use(path)   # keep every CDLL alive; `use` only re-points the binding
+    os.environ.update(envs[name])
+    t = torch.randn(1, 1, 4, 128, 64, device=dev).bfloat16().relu() + 1e-3      # general kernel (N = 512): reads the knobs
+    mhla_b200.mhla(t, t, t, torch.rand(4, 4, device=dev) / 4, normalize=True)
+    torch.cuda.synchronize()
+    for k_ in envs[name]:
+        del os.environ[k_]
 results = {}
 for sname in shape_sel:
     B, H, M, w, D, normalize, rope = SHAPES[sname]
