@@ -654,14 +654,16 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   DeviceState* dst = nullptr;
   int rc = device_state(&dst);
   if (rc != MHLA_OK) return rc;
-  int per_sm = 2048 / threads;                     // resident CTAs per SM by threads
-  if (per_sm > 8) per_sm = 8;
+  // persistent grid = exactly the CTAs that are resident at once (registers decide: ~4 per SM at 192 threads), so every
+  // CTA walks the same number of rows and there is no second wave
+  auto kern = d->in_dtype == 0 ? mhla::wan_prep_kernel<0> : (d->in_dtype == 1 ? mhla::wan_prep_kernel<1> : mhla::wan_prep_kernel<2>);
+  int per_sm = 0;
+  if (!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0), "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+    return MHLA_ERR_CUDA;
   if (per_sm < 1) per_sm = 1;
   const long long want = (long long)dst->sms * per_sm;
   const int grid = (int)(d->rows < want ? d->rows : want);
-  if (d->in_dtype == 0) mhla::wan_prep_kernel<0><<<grid, threads, 0, stream>>>(P);
-  else if (d->in_dtype == 1) mhla::wan_prep_kernel<1><<<grid, threads, 0, stream>>>(P);
-  else mhla::wan_prep_kernel<2><<<grid, threads, 0, stream>>>(P);
+  kern<<<grid, threads, 0, stream>>>(P);
   if (!cuda_ok(cudaGetLastError(), "wan_prep_kernel")) return MHLA_ERR_CUDA;
   g_last_launches = 1;
   return MHLA_OK;

@@ -56,35 +56,84 @@ __device__ __forceinline__ void store8(void* base, long long idx, const float (&
   *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + idx) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
 }
 
+// One row's 8 channels of one tensor as loaded (16 bytes of 16-bit data or 32 bytes of fp32): the conversion to float
+// happens when the row is consumed, so a prefetched row costs registers but never a scoreboard stall at issue time.
+template <int IN>
+struct Raw8 {
+  uint4 a, b;   // b: fp32 inputs only
+  __device__ __forceinline__ void load(const void* base, long long idx) {
+    if constexpr (IN == 2) {
+      const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + idx);
+      a = __ldg(p); b = __ldg(p + 1);
+    } else {
+      a = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + idx));
+    }
+  }
+  __device__ __forceinline__ void get(float (&f)[8]) const {
+    if constexpr (IN == 2) {
+      f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
+      f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
+    } else {
+      const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 t;
+        if constexpr (IN == 0) t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[i]));
+        else t = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+        f[2 * i] = t.x; f[2 * i + 1] = t.y;
+      }
+    }
+  }
+};
+
 template <int IN>
 __global__ void wan_prep_kernel(const WanPrepParams p) {
-  // Persistent over token rows (grid = a few CTAs per SM): the loads of the NEXT row are issued before the current row is
-  // reduced, normalised and stored, so every thread keeps two rows of reads in flight (one CTA per token left the
-  // memory system at 2.6 TB/s: each row's load -> block reduction -> store chain was fully exposed).
+  // Persistent over token rows (grid = a few CTAs per SM).  Every thread keeps the reads of its next TWO rows in flight
+  // as raw 16-byte registers (two register sets, loop unrolled by two - no register-to-register rotation that would wait
+  // for the load) while the current row is reduced, normalised, rotated and stored: 64 bytes per thread x 1536 threads
+  // per SM in flight.  History: one CTA per token left the memory system at 2.6 TB/s (load -> block reduction -> store
+  // chain fully exposed), one row of look-ahead whose conversion sat right behind the load at 2.9 TB/s.
   __shared__ float red[2][2][32];
   const int tid = threadIdx.x;
   const int c0 = tid * 8;
   const bool act = c0 < p.C;
   const int nw = (blockDim.x + 31) >> 5;
-  float wqv[8], wkv[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { wqv[i] = 1.f; wkv[i] = 1.f; }
-  if (act && p.wq) load8<2>(p.wq, c0, wqv);
-  if (act && p.wk) load8<2>(p.wk, c0, wkv);
-  float qn[8], kn[8];
+  const int G = (int)gridDim.x;
+  // (the RMSNorm weights are re-read per row - 64 bytes per thread from L1 - instead of living in 16 registers: the
+  //  register budget decides how many CTAs, i.e. how many rows in flight, an SM holds)
+  Raw8<IN> qa, ka, qb, kb;   // set a: rows blockIdx.x + 2nG, set b: rows blockIdx.x + (2n+1)G
+  qa.a = qa.b = ka.a = ka.b = qb.a = qb.b = kb.a = kb.b = make_uint4(0u, 0u, 0u, 0u);
+  // the token's rotation angles travel with the row's set: the tables are streamed from HBM once per launch (16 MB at the
+  // Wan size), and a load issued where the rotation needs it exposed a DRAM round trip per row (122 us for the layer)
+  float4 csa = make_float4(1.f, 1.f, 1.f, 1.f), sna = make_float4(0.f, 0.f, 0.f, 0.f), csb = csa, snb = sna;
+  const int d0 = c0 % p.D;                                       // 8 channels never straddle a head (D % 8 == 0)
+  auto load_angles = [&](long long r, float4& cs, float4& sn) {
+    if (p.cos_t == nullptr) return;
+    const long long tok = r % p.N;
+    cs = __ldg(reinterpret_cast<const float4*>(p.cos_t + tok * (p.D / 2) + d0 / 2));
+    sn = __ldg(reinterpret_cast<const float4*>(p.sin_t + tok * (p.D / 2) + d0 / 2));
+  };
   int row = blockIdx.x;
   if (act && row < p.rows) {
-    load8<IN>(p.xq, (long long)row * p.ld_in + c0, qn);
-    load8<IN>(p.xk, (long long)row * p.ld_in + c0, kn);
+    qa.load(p.xq, (long long)row * p.ld_in + c0);
+    ka.load(p.xk, (long long)row * p.ld_in + c0);
+    load_angles(row, csa, sna);
   }
-  for (int it = 0; row < p.rows; row += gridDim.x, ++it) {
+  if (act && row + G < p.rows) {
+    qb.load(p.xq, (long long)(row + G) * p.ld_in + c0);
+    kb.load(p.xk, (long long)(row + G) * p.ld_in + c0);
+    load_angles(row + G, csb, snb);
+  }
+  // one row: consume the register set, refill it with the row two steps ahead, then reduce / normalise / rotate / store
+  auto body = [&](const int r, Raw8<IN>& qr, Raw8<IN>& kr, float4& csr, float4& snr, const int it) {
     float q[8], k[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { q[i] = qn[i]; k[i] = kn[i]; }
-    const int nrow = row + gridDim.x;
+    qr.get(q); kr.get(k);
+    const float4 cs = csr, sn = snr;
+    const long long nrow = (long long)r + 2ll * G;
     if (act && nrow < p.rows) {
-      load8<IN>(p.xq, (long long)nrow * p.ld_in + c0, qn);
-      load8<IN>(p.xk, (long long)nrow * p.ld_in + c0, kn);
+      qr.load(p.xq, nrow * p.ld_in + c0);
+      kr.load(p.xk, nrow * p.ld_in + c0);
+      load_angles(nrow, csr, snr);
     }
     float sq = 0.f, sk = 0.f;
     if (act) {
@@ -96,23 +145,28 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
     float (*rd)[32] = red[it & 1];                 // alternate buffers: one barrier per row
     if ((tid & 31) == 0) { rd[0][tid >> 5] = sq; rd[1][tid >> 5] = sk; }
     __syncthreads();
-    if (!act) continue;
+    if (!act) return;
     sq = 0.f; sk = 0.f;
     for (int i = 0; i < nw; ++i) { sq += rd[0][i]; sk += rd[1][i]; }
     const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
     const float rk = p.wk ? rsqrtf(sk / (float)p.C + p.eps_norm) : 1.f;
+    {
+      float wv[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      q[i] = fmaxf(q[i] * rq * wqv[i], 0.f) + p.eps;
-      k[i] = fmaxf(k[i] * rk * wkv[i], 0.f) + p.eps;
+      for (int i = 0; i < 8; ++i) wv[i] = 1.f;
+      if (p.wq) load8<2>(p.wq, c0, wv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaxf(q[i] * rq * wv[i], 0.f) + p.eps;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wv[i] = 1.f;
+      if (p.wk) load8<2>(p.wk, c0, wv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = fmaxf(k[i] * rk * wv[i], 0.f) + p.eps;
     }
-    const long long o = (long long)row * p.C + c0;
+    const long long o = (long long)r * p.C + c0;
     if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
     if (p.cos_t) {
       // interleaved-pair rotation (view_as_complex, mhla_utils.py:144-151): pair i of a head takes angle [token, i]
-      const int tok = row % p.N, d0 = c0 % p.D;                  // 8 channels never straddle a head (D % 8 == 0)
-      const float4 cs = __ldg(reinterpret_cast<const float4*>(p.cos_t + (long long)tok * (p.D / 2) + d0 / 2));
-      const float4 sn = __ldg(reinterpret_cast<const float4*>(p.sin_t + (long long)tok * (p.D / 2) + d0 / 2));
       const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -123,6 +177,13 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
     }
     store8(p.q_rope, o, q, p.out_fp16);
     store8(p.k_rope, o, k, p.out_fp16);
+  };
+  for (int it = 0; row < p.rows; it += 2) {
+    body(row, qa, ka, csa, sna, it);
+    row += G;
+    if (row >= p.rows) break;
+    body(row, qb, kb, csb, snb, it + 1);
+    row += G;
   }
 }
 
