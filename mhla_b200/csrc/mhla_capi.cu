@@ -654,16 +654,26 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   DeviceState* dst = nullptr;
   int rc = device_state(&dst);
   if (rc != MHLA_OK) return rc;
-  // persistent grid = exactly the CTAs that are resident at once (registers decide: ~4 per SM at 192 threads), so every
-  // CTA walks the same number of rows and there is no second wave
+  // shared-memory ring of staged rows (see the kernel): as many stages as fit 47 KB (no opt-in needed), at most 8, at
+  // least 2 - very wide fp32 rows take the opt-in; persistent grid = exactly the CTAs that are resident at once
   auto kern = d->in_dtype == 0 ? mhla::wan_prep_kernel<0> : (d->in_dtype == 1 ? mhla::wan_prep_kernel<1> : mhla::wan_prep_kernel<2>);
+  const size_t rowb = (size_t)d->C * (d->in_dtype == 2 ? 4 : 2), angb = d->cos_table ? (size_t)d->D * 2 : 0;
+  const size_t stage = align_up(2 * rowb + 2 * angb, 128);
+  int stages = (int)((47 * 1024) / stage);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
+  const size_t smem = stages * stage + 8 * (size_t)stages;
+  if (smem > 48 * 1024 &&
+      !cuda_ok(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute(wan_prep)"))
+    return MHLA_ERR_CUDA;
+  P.stages = stages; P.stage_bytes = (int)stage;
   int per_sm = 0;
-  if (!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, 0), "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
+  if (!cuda_ok(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem), "cudaOccupancyMaxActiveBlocksPerMultiprocessor"))
     return MHLA_ERR_CUDA;
   if (per_sm < 1) per_sm = 1;
   const long long want = (long long)dst->sms * per_sm;
   const int grid = (int)(d->rows < want ? d->rows : want);
-  kern<<<grid, threads, 0, stream>>>(P);
+  kern<<<grid, threads, smem, stream>>>(P);
   if (!cuda_ok(cudaGetLastError(), "wan_prep_kernel")) return MHLA_ERR_CUDA;
   g_last_launches = 1;
   return MHLA_OK;

@@ -12,6 +12,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "ptx.cuh"
+
 namespace mhla {
 
 struct WanPrepParams {
@@ -24,6 +26,7 @@ struct WanPrepParams {
   int rows, N, C, D;                       // rows = B*N
   int in_dtype;                            // 0 bf16, 1 fp16, 2 fp32
   int out_fp16;
+  int stages, stage_bytes;                 // shared-memory ring of staged rows: [xq row | xk row | cos row | sin row] per stage
   float eps_norm, eps;
 };
 
@@ -56,96 +59,105 @@ __device__ __forceinline__ void store8(void* base, long long idx, const float (&
   *reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + idx) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
 }
 
-// One row's 8 channels of one tensor as loaded (16 bytes of 16-bit data or 32 bytes of fp32): the conversion to float
-// happens when the row is consumed, so a prefetched row costs registers but never a scoreboard stall at issue time.
+// 8 consecutive channels of a staged row (shared memory) as floats
 template <int IN>
-struct Raw8 {
-  uint4 a, b;   // b: fp32 inputs only
-  __device__ __forceinline__ void load(const void* base, long long idx) {
-    if constexpr (IN == 2) {
-      const uint4* p = reinterpret_cast<const uint4*>(static_cast<const float*>(base) + idx);
-      a = __ldg(p); b = __ldg(p + 1);
-    } else {
-      a = __ldg(reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(base) + idx));
-    }
-  }
-  __device__ __forceinline__ void get(float (&f)[8]) const {
-    if constexpr (IN == 2) {
-      f[0] = __uint_as_float(a.x); f[1] = __uint_as_float(a.y); f[2] = __uint_as_float(a.z); f[3] = __uint_as_float(a.w);
-      f[4] = __uint_as_float(b.x); f[5] = __uint_as_float(b.y); f[6] = __uint_as_float(b.z); f[7] = __uint_as_float(b.w);
-    } else {
-      const uint32_t w4[4] = {a.x, a.y, a.z, a.w};
+__device__ __forceinline__ void smem_get8(const uint8_t* rowp, int c0, float (&f)[8]) {
+  if constexpr (IN == 2) {
+    const float4 a = *reinterpret_cast<const float4*>(rowp + c0 * 4), b = *reinterpret_cast<const float4*>(rowp + c0 * 4 + 16);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  } else {
+    const uint4 u = *reinterpret_cast<const uint4*>(rowp + c0 * 2);
+    const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float2 t;
-        if constexpr (IN == 0) t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[i]));
-        else t = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
-        f[2 * i] = t.x; f[2 * i + 1] = t.y;
-      }
+    for (int i = 0; i < 4; ++i) {
+      float2 t;
+      if constexpr (IN == 0) t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w4[i]));
+      else t = __half22float2(*reinterpret_cast<const __half2*>(&w4[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
     }
   }
-};
+}
+
+// global -> shared bulk copy (TMA, 1-D), completion counted in bytes on an mbarrier; 16-byte aligned, size % 16 == 0
+__device__ __forceinline__ void prep_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 
 template <int IN>
 __global__ void wan_prep_kernel(const WanPrepParams p) {
-  // Persistent over token rows (grid = a few CTAs per SM).  Every thread keeps the reads of its next TWO rows in flight
-  // as raw 16-byte registers (two register sets, loop unrolled by two - no register-to-register rotation that would wait
-  // for the load) while the current row is reduced, normalised, rotated and stored: 64 bytes per thread x 1536 threads
-  // per SM in flight.  History: one CTA per token left the memory system at 2.6 TB/s (load -> block reduction -> store
-  // chain fully exposed), one row of look-ahead whose conversion sat right behind the load at 2.9 TB/s.
+  // Persistent over token rows.  The rows are STAGED: one thread issues bulk copies (TMA) of the next `stages` rows of
+  // xq, xk and of the tokens' cos / sin rows into a shared-memory ring, completion on one mbarrier per stage; the CTA
+  // reads a landed row, reduces, normalises, rotates and stores it, and the reduction's own __syncthreads is the point
+  // after which the stage is refilled.  Bytes in flight per SM = CTAs x (stages - 1) x 6.5 KB (Wan) - not bounded by
+  // registers.  History (Wan layer, B = 1): one CTA per token 2.6 TB/s; one / two rows of register look-ahead 130 / 103 us
+  // (a load takes ~3 us under the kernel's own traffic, 64 B per thread in flight were not enough).
+  extern __shared__ __align__(128) uint8_t prep_smem[];
   __shared__ float red[2][2][32];
   const int tid = threadIdx.x;
   const int c0 = tid * 8;
   const bool act = c0 < p.C;
   const int nw = (blockDim.x + 31) >> 5;
   const int G = (int)gridDim.x;
-  // (the RMSNorm weights are re-read per row - 64 bytes per thread from L1 - instead of living in 16 registers: the
-  //  register budget decides how many CTAs, i.e. how many rows in flight, an SM holds)
-  Raw8<IN> qa, ka, qb, kb;   // set a: rows blockIdx.x + 2nG, set b: rows blockIdx.x + (2n+1)G
-  qa.a = qa.b = ka.a = ka.b = qb.a = qb.b = kb.a = kb.b = make_uint4(0u, 0u, 0u, 0u);
-  // the token's rotation angles travel with the row's set: the tables are streamed from HBM once per launch (16 MB at the
-  // Wan size), and a load issued where the rotation needs it exposed a DRAM round trip per row (122 us for the layer)
-  float4 csa = make_float4(1.f, 1.f, 1.f, 1.f), sna = make_float4(0.f, 0.f, 0.f, 0.f), csb = csa, snb = sna;
-  const int d0 = c0 % p.D;                                       // 8 channels never straddle a head (D % 8 == 0)
-  auto load_angles = [&](long long r, float4& cs, float4& sn) {
-    if (p.cos_t == nullptr) return;
-    const long long tok = r % p.N;
-    cs = __ldg(reinterpret_cast<const float4*>(p.cos_t + tok * (p.D / 2) + d0 / 2));
-    sn = __ldg(reinterpret_cast<const float4*>(p.sin_t + tok * (p.D / 2) + d0 / 2));
+  const int S = p.stages;
+  const uint32_t rowb = (uint32_t)p.C * (IN == 2 ? 4u : 2u);           // bytes of one input row
+  const uint32_t angb = p.cos_t ? (uint32_t)p.D * 2u : 0u;             // bytes of one cos (or sin) row: D/2 floats
+  uint64_t* bars = reinterpret_cast<uint64_t*>(prep_smem + (size_t)S * p.stage_bytes);
+  const int d0 = c0 % p.D;                                             // 8 channels never straddle a head (D % 8 == 0)
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int s, long long r) {   // thread 0
+    uint8_t* st = prep_smem + (size_t)s * p.stage_bytes;
+    mbar_arrive_expect_tx(&bars[s], 2u * rowb + 2u * angb);
+    prep_bulk_load(st, static_cast<const uint8_t*>(p.xq) + (size_t)r * p.ld_in * (IN == 2 ? 4 : 2), rowb, &bars[s]);
+    prep_bulk_load(st + rowb, static_cast<const uint8_t*>(p.xk) + (size_t)r * p.ld_in * (IN == 2 ? 4 : 2), rowb, &bars[s]);
+    if (angb) {
+      const long long tok = r % p.N;
+      prep_bulk_load(st + 2 * rowb, p.cos_t + tok * (p.D / 2), angb, &bars[s]);
+      prep_bulk_load(st + 2 * rowb + angb, p.sin_t + tok * (p.D / 2), angb, &bars[s]);
+    }
   };
   int row = blockIdx.x;
-  if (act && row < p.rows) {
-    qa.load(p.xq, (long long)row * p.ld_in + c0);
-    ka.load(p.xk, (long long)row * p.ld_in + c0);
-    load_angles(row, csa, sna);
-  }
-  if (act && row + G < p.rows) {
-    qb.load(p.xq, (long long)(row + G) * p.ld_in + c0);
-    kb.load(p.xk, (long long)(row + G) * p.ld_in + c0);
-    load_angles(row + G, csb, snb);
-  }
-  // one row: consume the register set, refill it with the row two steps ahead, then reduce / normalise / rotate / store
-  auto body = [&](const int r, Raw8<IN>& qr, Raw8<IN>& kr, float4& csr, float4& snr, const int it) {
+  if (tid == 0)
+    for (int s = 0; s < S; ++s)
+      if ((long long)row + (long long)s * G < p.rows) issue(s, (long long)row + (long long)s * G);
+  for (int it = 0; row < p.rows; row += G, ++it) {
+    const int s = it % S;
+    const uint8_t* st = prep_smem + (size_t)s * p.stage_bytes;
+    mbar_wait(&bars[s], (uint32_t)(it / S) & 1u);
     float q[8], k[8];
-    qr.get(q); kr.get(k);
-    const float4 cs = csr, sn = snr;
-    const long long nrow = (long long)r + 2ll * G;
-    if (act && nrow < p.rows) {
-      qr.load(p.xq, nrow * p.ld_in + c0);
-      kr.load(p.xk, nrow * p.ld_in + c0);
-      load_angles(nrow, csr, snr);
-    }
+    float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), sn = make_float4(0.f, 0.f, 0.f, 0.f);
     float sq = 0.f, sk = 0.f;
     if (act) {
+      smem_get8<IN>(st, c0, q);
+      smem_get8<IN>(st + rowb, c0, k);
+      if (angb) {
+        cs = *reinterpret_cast<const float4*>(st + 2 * rowb + (d0 / 2) * 4);
+        sn = *reinterpret_cast<const float4*>(st + 2 * rowb + angb + (d0 / 2) * 4);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) { sq = fmaf(q[i], q[i], sq); sk = fmaf(k[i], k[i], sk); }
+      // (the angle loads must have RETURNED before the barrier below frees the stage: make their results live here)
+      asm volatile("" ::"f"(cs.x), "f"(cs.w), "f"(sn.x), "f"(sn.w));
     }
     // block-wide sums of squares (the norm runs over the FULL channel dim, across heads: wan/model.py:181-196)
     for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
     float (*rd)[32] = red[it & 1];                 // alternate buffers: one barrier per row
     if ((tid & 31) == 0) { rd[0][tid >> 5] = sq; rd[1][tid >> 5] = sk; }
-    __syncthreads();
-    if (!act) return;
+    __syncthreads();                               // ... which also says: every thread has read stage s
+    if (tid == 0) {
+      const long long nr = (long long)row + (long long)S * G;
+      if (nr < p.rows) {
+        fence_proxy_async_smem();                  // generic-proxy reads of the stage before the async-proxy refill
+        issue(s, nr);
+      }
+    }
+    if (!act) continue;
     sq = 0.f; sk = 0.f;
     for (int i = 0; i < nw; ++i) { sq += rd[0][i]; sk += rd[1][i]; }
     const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
@@ -163,9 +175,9 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) k[i] = fmaxf(k[i] * rk * wv[i], 0.f) + p.eps;
     }
-    const long long o = (long long)r * p.C + c0;
+    const long long o = (long long)row * p.C + c0;
     if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
-    if (p.cos_t) {
+    if (angb) {
       // interleaved-pair rotation (view_as_complex, mhla_utils.py:144-151): pair i of a head takes angle [token, i]
       const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
 #pragma unroll
@@ -177,13 +189,6 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
     }
     store8(p.q_rope, o, q, p.out_fp16);
     store8(p.k_rope, o, k, p.out_fp16);
-  };
-  for (int it = 0; row < p.rows; it += 2) {
-    body(row, qa, ka, csa, sna, it);
-    row += G;
-    if (row >= p.rows) break;
-    body(row, qb, kb, csb, snb, it + 1);
-    row += G;
   }
 }
 

@@ -33,6 +33,25 @@ def timed(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
+def timed_graph(fn, reps=10):
+    """Device time per call with the Python / ctypes / allocator cost off the timed path: `reps` calls in ONE CUDA graph."""
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        for _ in range(reps):
+            fn()
+    gr.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    gr.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e3
+
+
 dim, heads, layout, grid = 1536, 12, (3, 5, 10), (21, 30, 50)
 N = grid[0] * grid[1] * grid[2]
 freqs = rope_freqs(dim // heads)
@@ -54,10 +73,11 @@ for B, norm in ((1, False), (2, False), (2, True)):
         t_op = timed(lambda: mhla_b200.mhla_blockmix_grid(q, q, q, W, grid, layout, normalize=False))
         cos, sin = _rope_tables(grid, freqs, x.device)
         xq = torch.randn(B, N, dim, device="cuda").bfloat16()
-        t_prep = timed(lambda: mhla_b200.wan_prep(xq, xq, m.norm_q.weight, m.norm_k.weight, cos, sin, dim // heads, want_plain=norm))
+        xk = torch.randn(B, N, dim, device="cuda").bfloat16()
+        t_prep = timed_graph(lambda: mhla_b200.wan_prep(xq, xk, m.norm_q.weight, m.norm_k.weight, cos, sin, dim // heads, want_plain=norm))
     err = float((y1.float() - y2.float()).norm() / y2.float().norm())
     print(f"B={B} normalize_out={norm}: module forward fused {t_fast:.0f} us vs reference-style {t_slow:.0f} us "
-          f"({t_slow / t_fast:.2f}x), rel diff {err:.2e}; operator (3-D view, no norm) {t_op:.0f} us, prep kernel {t_prep:.0f} us")
+          f"({t_slow / t_fast:.2f}x), rel diff {err:.2e}; operator (3-D view, no norm) {t_op:.0f} us, prep kernel (CUDA-graph device time, distinct q / k inputs) {t_prep:.1f} us")
 
 # gate + LePE (MHLA_Video_Uni(is_gated, is_lepe) = Gated_MHLA_Video_LePE's post-processing): SiLU gate and "+ lepe" inside
 # the readout epilogue (ABI v4) against the same fused path with those two as separate elementwise passes
