@@ -650,7 +650,7 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   P.rows = d->rows; P.N = d->N; P.C = d->C; P.D = d->D; P.in_dtype = d->in_dtype; P.out_fp16 = d->out_dtype == MHLA_FP16;
   P.eps_norm = d->eps_norm; P.eps = d->eps;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  const int threads = ((d->C / 8) + 31) / 32 * 32;
+  const int threads = (((d->C / 8) + 1) / 2 + 31) / 32 * 32;   // two 8-channel chunks per thread
   DeviceState* dst = nullptr;
   int rc = device_state(&dst);
   if (rc != MHLA_OK) return rc;
@@ -660,7 +660,7 @@ int mhla_wan_prep(const mhla_wan_prep_desc* d, void* stream_) {
   const size_t rowb = (size_t)d->C * (d->in_dtype == 2 ? 4 : 2), angb = d->cos_table ? (size_t)d->D * 2 : 0;
   const size_t stage = align_up(2 * rowb + 2 * angb, 128);
   int stages = (int)((47 * 1024) / stage);
-  if (stages > 8) stages = 8;
+  if (stages > 4) stages = 4;     // (the kernel is issue-bound, not latency-bound: more CTAs per SM beat deeper rings)
   if (stages < 2) stages = 2;
   const size_t smem = stages * stage + 8 * (size_t)stages;
   if (smem > 48 * 1024 &&

@@ -91,92 +91,79 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
   // Persistent over token rows.  The rows are STAGED: one thread issues bulk copies (TMA) of the next `stages` rows of
   // xq, xk and of the tokens' cos / sin rows into a shared-memory ring, completion on one mbarrier per stage; the CTA
   // reads a landed row, reduces, normalises, rotates and stores it, and the reduction's own __syncthreads is the point
-  // after which the stage is refilled.  Bytes in flight per SM = CTAs x (stages - 1) x 6.5 KB (Wan) - not bounded by
-  // registers.  History (Wan layer, B = 1): one CTA per token 2.6 TB/s; one / two rows of register look-ahead 130 / 103 us
-  // (a load takes ~3 us under the kernel's own traffic, 64 B per thread in flight were not enough).
+  // after which the stage is refilled.
+  // ncu on the first ring version (profiles/r02c_wanprep_ncu_details_ring.txt): 43 % DRAM throughput but IPC 2.8 - the
+  // kernel is ISSUE-bound, ~390 instructions per thread and row for 8 channels.  Hence: 16 channels (two 16-byte chunks,
+  // blockDim apart) per thread so that the per-row fixed cost (mbarrier wait, shuffles, block reduction, rsqrt) is paid by
+  // half as many threads; ring stage / phase, row pointers and the token index advance by additions (no 64-bit
+  // multiplies, no integer divisions in the loop); relu(x * r * w) = relu(x * w) * r as FMUL + FMNMX + FFMA.
+  // History (Wan layer, B = 1): one CTA per token 2.6 TB/s; one / two rows of register look-ahead 130 / 103 us; ring 98 us.
   extern __shared__ __align__(128) uint8_t prep_smem[];
-  __shared__ float red[2][2][32];
+  __shared__ float2 red[2][32];
   const int tid = threadIdx.x;
-  const int c0 = tid * 8;
-  const bool act = c0 < p.C;
+  const int nchunk = p.C >> 3;
+  const int cA = tid * 8, cB = (tid + (int)blockDim.x) * 8;            // first channels of this thread's two chunks
+  const bool actA = tid < nchunk, actB = tid + (int)blockDim.x < nchunk;
   const int nw = (blockDim.x + 31) >> 5;
   const int G = (int)gridDim.x;
   const int S = p.stages;
-  const uint32_t rowb = (uint32_t)p.C * (IN == 2 ? 4u : 2u);           // bytes of one input row
+  constexpr int kEsz = IN == 2 ? 4 : 2;
+  const uint32_t rowb = (uint32_t)p.C * kEsz;                          // bytes of one input row
   const uint32_t angb = p.cos_t ? (uint32_t)p.D * 2u : 0u;             // bytes of one cos (or sin) row: D/2 floats
   uint64_t* bars = reinterpret_cast<uint64_t*>(prep_smem + (size_t)S * p.stage_bytes);
-  const int d0 = c0 % p.D;                                             // 8 channels never straddle a head (D % 8 == 0)
+  const int aA = (cA % p.D) * 2, aB = (cB % p.D) * 2;                  // byte offset of the chunk's 4 angles in a cos row
   if (tid == 0) {
     for (int s = 0; s < S; ++s) mbar_init(&bars[s], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  auto issue = [&](int s, long long r) {   // thread 0
+  // producer state (thread 0): next row to stage, its token, its source pointers - all advanced by additions
+  const size_t in_step = (size_t)G * p.ld_in * kEsz;
+  long long irow = blockIdx.x;
+  int itok = (int)(irow % p.N);
+  const int gmod = G % p.N;
+  const uint8_t* iq = static_cast<const uint8_t*>(p.xq) + (size_t)irow * p.ld_in * kEsz;
+  const uint8_t* ik = static_cast<const uint8_t*>(p.xk) + (size_t)irow * p.ld_in * kEsz;
+  auto issue = [&](int s) {   // thread 0: stage row `irow` into stage s (caller checked irow < rows), then advance
     uint8_t* st = prep_smem + (size_t)s * p.stage_bytes;
     mbar_arrive_expect_tx(&bars[s], 2u * rowb + 2u * angb);
-    prep_bulk_load(st, static_cast<const uint8_t*>(p.xq) + (size_t)r * p.ld_in * (IN == 2 ? 4 : 2), rowb, &bars[s]);
-    prep_bulk_load(st + rowb, static_cast<const uint8_t*>(p.xk) + (size_t)r * p.ld_in * (IN == 2 ? 4 : 2), rowb, &bars[s]);
+    prep_bulk_load(st, iq, rowb, &bars[s]);
+    prep_bulk_load(st + rowb, ik, rowb, &bars[s]);
     if (angb) {
-      const long long tok = r % p.N;
-      prep_bulk_load(st + 2 * rowb, p.cos_t + tok * (p.D / 2), angb, &bars[s]);
-      prep_bulk_load(st + 2 * rowb + angb, p.sin_t + tok * (p.D / 2), angb, &bars[s]);
+      prep_bulk_load(st + 2 * rowb, p.cos_t + (size_t)itok * (p.D / 2), angb, &bars[s]);
+      prep_bulk_load(st + 2 * rowb + angb, p.sin_t + (size_t)itok * (p.D / 2), angb, &bars[s]);
     }
+    irow += G; iq += in_step; ik += in_step;
+    itok += gmod; if (itok >= p.N) itok -= p.N;
   };
-  int row = blockIdx.x;
   if (tid == 0)
-    for (int s = 0; s < S; ++s)
-      if ((long long)row + (long long)s * G < p.rows) issue(s, (long long)row + (long long)s * G);
-  for (int it = 0; row < p.rows; row += G, ++it) {
-    const int s = it % S;
-    const uint8_t* st = prep_smem + (size_t)s * p.stage_bytes;
-    mbar_wait(&bars[s], (uint32_t)(it / S) & 1u);
-    float q[8], k[8];
-    float4 cs = make_float4(1.f, 1.f, 1.f, 1.f), sn = make_float4(0.f, 0.f, 0.f, 0.f);
-    float sq = 0.f, sk = 0.f;
-    if (act) {
-      smem_get8<IN>(st, c0, q);
-      smem_get8<IN>(st + rowb, c0, k);
-      if (angb) {
-        cs = *reinterpret_cast<const float4*>(st + 2 * rowb + (d0 / 2) * 4);
-        sn = *reinterpret_cast<const float4*>(st + 2 * rowb + angb + (d0 / 2) * 4);
-      }
+    for (int s = 0; s < S && irow < p.rows; ++s) issue(s);
+  // consumer state: output element offset of this row's first channel, ring stage and phase
+  size_t orow = (size_t)blockIdx.x * p.C;
+  const size_t out_step = (size_t)G * p.C;
+  int s = 0;
+  uint32_t ph = 0;
+  uint32_t flip = 0;
+  // one 8-channel chunk: normalise + relu + eps, optional plain store, rotation, roped store
+  auto finish = [&](float (&q)[8], float (&k)[8], const float4& cs, const float4& sn, int c0, float rq, float rk, size_t o) {
+    float wv[8];
+    if (p.wq) {
+      load8<2>(p.wq, c0, wv);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sq = fmaf(q[i], q[i], sq); sk = fmaf(k[i], k[i], sk); }
-      // (the angle loads must have RETURNED before the barrier below frees the stage: make their results live here)
-      asm volatile("" ::"f"(cs.x), "f"(cs.w), "f"(sn.x), "f"(sn.w));
+      for (int i = 0; i < 8; ++i) q[i] = fmaf(fmaxf(q[i] * wv[i], 0.f), rq, p.eps);   // relu(x r w) = relu(x w) r, r > 0
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = fmaxf(q[i], 0.f) + p.eps;
     }
-    // block-wide sums of squares (the norm runs over the FULL channel dim, across heads: wan/model.py:181-196)
-    for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
-    float (*rd)[32] = red[it & 1];                 // alternate buffers: one barrier per row
-    if ((tid & 31) == 0) { rd[0][tid >> 5] = sq; rd[1][tid >> 5] = sk; }
-    __syncthreads();                               // ... which also says: every thread has read stage s
-    if (tid == 0) {
-      const long long nr = (long long)row + (long long)S * G;
-      if (nr < p.rows) {
-        fence_proxy_async_smem();                  // generic-proxy reads of the stage before the async-proxy refill
-        issue(s, nr);
-      }
+    if (p.wk) {
+      load8<2>(p.wk, c0, wv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = fmaf(fmaxf(k[i] * wv[i], 0.f), rk, p.eps);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) k[i] = fmaxf(k[i], 0.f) + p.eps;
     }
-    if (!act) continue;
-    sq = 0.f; sk = 0.f;
-    for (int i = 0; i < nw; ++i) { sq += rd[0][i]; sk += rd[1][i]; }
-    const float rq = p.wq ? rsqrtf(sq / (float)p.C + p.eps_norm) : 1.f;
-    const float rk = p.wk ? rsqrtf(sk / (float)p.C + p.eps_norm) : 1.f;
-    {
-      float wv[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) wv[i] = 1.f;
-      if (p.wq) load8<2>(p.wq, c0, wv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[i] = fmaxf(q[i] * rq * wv[i], 0.f) + p.eps;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) wv[i] = 1.f;
-      if (p.wk) load8<2>(p.wk, c0, wv);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) k[i] = fmaxf(k[i] * rk * wv[i], 0.f) + p.eps;
-    }
-    const long long o = (long long)row * p.C + c0;
-    if (p.q_plain) { store8(p.q_plain, o, q, p.out_fp16); store8(p.k_plain, o, k, p.out_fp16); }
+    if (p.q_plain) { store8(p.q_plain, (long long)o, q, p.out_fp16); store8(p.k_plain, (long long)o, k, p.out_fp16); }
     if (angb) {
       // interleaved-pair rotation (view_as_complex, mhla_utils.py:144-151): pair i of a head takes angle [token, i]
       const float c4[4] = {cs.x, cs.y, cs.z, cs.w}, s4[4] = {sn.x, sn.y, sn.z, sn.w};
@@ -187,8 +174,57 @@ __global__ void wan_prep_kernel(const WanPrepParams p) {
         k[2 * i] = a2 * c4[i] - b2 * s4[i]; k[2 * i + 1] = a2 * s4[i] + b2 * c4[i];
       }
     }
-    store8(p.q_rope, o, q, p.out_fp16);
-    store8(p.k_rope, o, k, p.out_fp16);
+    store8(p.q_rope, (long long)o, q, p.out_fp16);
+    store8(p.k_rope, (long long)o, k, p.out_fp16);
+  };
+  for (long long row = blockIdx.x; row < p.rows; row += G) {
+    const uint8_t* st = prep_smem + (size_t)s * p.stage_bytes;
+    mbar_wait(&bars[s], ph);
+    float qa[8], ka[8], qb[8], kb[8];
+    float4 csa = make_float4(1.f, 1.f, 1.f, 1.f), sna = make_float4(0.f, 0.f, 0.f, 0.f), csb = csa, snb = sna;
+    float sq = 0.f, sk = 0.f;
+    if (actA) {
+      smem_get8<IN>(st, cA, qa);
+      smem_get8<IN>(st + rowb, cA, ka);
+      if (angb) {
+        csa = *reinterpret_cast<const float4*>(st + 2 * rowb + aA);
+        sna = *reinterpret_cast<const float4*>(st + 2 * rowb + angb + aA);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sq = fmaf(qa[i], qa[i], sq); sk = fmaf(ka[i], ka[i], sk); }
+    }
+    if (actB) {
+      smem_get8<IN>(st, cB, qb);
+      smem_get8<IN>(st + rowb, cB, kb);
+      if (angb) {
+        csb = *reinterpret_cast<const float4*>(st + 2 * rowb + aB);
+        snb = *reinterpret_cast<const float4*>(st + 2 * rowb + angb + aB);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { sq = fmaf(qb[i], qb[i], sq); sk = fmaf(kb[i], kb[i], sk); }
+    }
+    // (the angle loads must have RETURNED before the barrier below frees the stage: make their results live here)
+    asm volatile("" ::"f"(csa.x), "f"(sna.x), "f"(csb.x), "f"(snb.x));
+    // block-wide sums of squares (the norm runs over the FULL channel dim, across heads: wan/model.py:181-196)
+    for (int o = 16; o > 0; o >>= 1) { sq += __shfl_xor_sync(0xffffffffu, sq, o); sk += __shfl_xor_sync(0xffffffffu, sk, o); }
+    float2* rd = red[flip];                        // alternate buffers: one barrier per row
+    if ((tid & 31) == 0) rd[tid >> 5] = make_float2(sq, sk);
+    __syncthreads();                               // ... which also says: every thread has read stage s
+    if (tid == 0 && irow < p.rows) {
+      fence_proxy_async_smem();                    // generic-proxy reads of the stage before the async-proxy refill
+      issue(s);
+    }
+    sq = 0.f; sk = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < nw; ++i) { const float2 t = rd[i]; sq += t.x; sk += t.y; }
+    const float inv_c = 1.0f / (float)p.C;
+    const float rq = p.wq ? rsqrtf(fmaf(sq, inv_c, p.eps_norm)) : 1.f;
+    const float rk = p.wk ? rsqrtf(fmaf(sk, inv_c, p.eps_norm)) : 1.f;
+    if (actA) finish(qa, ka, csa, sna, cA, rq, rk, orow + cA);
+    if (actB) finish(qb, kb, csb, snb, cB, rq, rk, orow + cB);
+    orow += out_step;
+    flip ^= 1u;
+    if (++s == S) { s = 0; ph ^= 1u; }
   }
 }
 
