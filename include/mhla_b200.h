@@ -256,6 +256,23 @@ typedef struct mhla_gate_add_desc {
 } mhla_gate_add_desc;
 int mhla_gate_add(const mhla_gate_add_desc* desc, void* stream);
 
+/*
+ * LePE of the Wan layers: the depthwise 3x3x3 convolution `self.lepe = nn.Conv3d(dim, dim, 3, padding=1, groups=dim)`
+ * applied to v (mhla_videogen/diffusion/model/wan/mhla_utils.py:289-296, wan/model.py `lepe`), computed on the token-major
+ * [B, F*H*W, C] tensor without the NCDHW rearrangements:
+ *   out[b, (f,h,w), c] = bias[c] + sum_{kf,kh,kw in 0..2} wt[(kf*3+kh)*3+kw][c] * x[b, (f+kf-1, h+kh-1, w+kw-1), c]   (zero padding)
+ * x: 16-bit, row pitch ld_x elements; wt: fp32 [27][C] (the Conv3d weight [C,1,3,3,3] transposed); bias fp32 [C] or NULL;
+ * out: [B, F*H*W, C] contiguous, dtype of x.  C % 8 == 0.
+ */
+typedef struct mhla_dwconv3d_desc {
+  int32_t B, F, H, W, C, dtype;
+  const void* x; int64_t ld_x;
+  const float* wt;
+  const float* bias;
+  void* out;
+} mhla_dwconv3d_desc;
+int mhla_dwconv3d(const mhla_dwconv3d_desc* desc, void* stream);
+
 /* Misc. */
 int mhla_abi_version(void);
 const char* mhla_strerror(int status);

@@ -22,7 +22,7 @@ FLAG_NO_SMALLN = 1 << 15
 
 EXPORTS = [
     "mhla_abi_version", "mhla_strerror", "mhla_last_cuda_error", "mhla_last_launch_count",
-    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal", "mhla_wan_prep", "mhla_bwd_prep", "mhla_bwd_post", "mhla_block_wsum", "mhla_gated_rmsnorm", "mhla_gate_add",
+    "mhla_blockmix_workspace_bytes", "mhla_blockmix_needs_workspace", "mhla_blockmix_workspace_layout", "mhla_fwd_blockmix", "mhla_blockmix_workspace_init", "mhla_causal_workspace_bytes", "mhla_fwd_causal", "mhla_wan_prep", "mhla_bwd_prep", "mhla_bwd_post", "mhla_block_wsum", "mhla_gated_rmsnorm", "mhla_gate_add", "mhla_dwconv3d",
 ]
 
 
@@ -95,6 +95,11 @@ class GateAddDesc(C.Structure):
                 ("out", C.c_void_p), ("ld_out", C.c_int64)]
 
 
+class DwConv3dDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("F", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("dtype", C.c_int32),
+                ("x", C.c_void_p), ("ld_x", C.c_int64), ("wt", C.c_void_p), ("bias", C.c_void_p), ("out", C.c_void_p)]
+
+
 class MhlaError(RuntimeError):
     pass
 
@@ -148,6 +153,9 @@ def lib() -> C.CDLL:
         if hasattr(L, "mhla_gate_add"):
             L.mhla_gate_add.restype = C.c_int
             L.mhla_gate_add.argtypes = [C.POINTER(GateAddDesc), C.c_void_p]
+        if hasattr(L, "mhla_dwconv3d"):
+            L.mhla_dwconv3d.restype = C.c_int
+            L.mhla_dwconv3d.argtypes = [C.POINTER(DwConv3dDesc), C.c_void_p]
         if L.mhla_abi_version() != 4:
             raise ImportError("libmhla_b200.so ABI version mismatch; rebuild with `python -m mhla_b200.build --force`")
         _lib = L

@@ -93,4 +93,67 @@ __global__ void __launch_bounds__(256) gate_add_kernel(const GateAddParams p) {
   }
 }
 
+// LePE of the Wan layers (mhla_videogen/diffusion/model/wan/model.py: `self.lepe = nn.Conv3d(dim, dim, 3, padding=1,
+// groups=dim)` applied to v, mhla_utils.py:289-296): a depthwise 3x3x3 convolution over the (F, H, W) token grid, computed
+// directly on the TOKEN-major [B, F*H*W, C] tensor the v projection produces and written token-major - what the operator's
+// post-op consumes.  The reference path rearranges to NCDHW, runs cuDNN's depthwise Conv3d (10 ms at the Wan size on a B200)
+// and rearranges back (a transposing copy).  Here: one thread per (token, 8 channels), 27 taps with zero padding, each tap
+// a 16-byte load of the neighbour token's channels (coalesced across the warp, L1/L2 hits for 26 of 27) and 8 FMAs with
+// the tap's weights from a [27][C] fp32 table; fp32 accumulation, bias, one rounding.
+struct DwConv3dParams {
+  const void* x; void* out;           // [B, F*H*W, C] 16-bit; x row pitch ld_x elements, out contiguous
+  const float* wt;                    // [27][C] fp32: wt[(kf*3 + kh)*3 + kw][c] = conv.weight[c, 0, kf, kh, kw]
+  const float* bias;                  // [C] fp32 or NULL
+  long long ld_x;
+  int B, F, H, W, C, fp16;
+};
+
+__global__ void __launch_bounds__(256) dwconv3d_kernel(const DwConv3dParams p) {
+  const int vec = p.C / 8;
+  const long long ntok = (long long)p.B * p.F * p.H * p.W;
+  const long long total = ntok * vec;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+    const long long tok = idx / vec;
+    const int c = (int)(idx - tok * vec) * 8;
+    long long t = tok;
+    const int w = (int)(t % p.W); t /= p.W;
+    const int h = (int)(t % p.H); t /= p.H;
+    const int f = (int)(t % p.F);
+    float acc[8];
+    if (p.bias) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+      acc[0] = b0.x; acc[1] = b0.y; acc[2] = b0.z; acc[3] = b0.w; acc[4] = b1.x; acc[5] = b1.y; acc[6] = b1.z; acc[7] = b1.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    }
+#pragma unroll
+    for (int kf = 0; kf < 3; ++kf) {
+      const int ff = f + kf - 1;
+      if (ff < 0 || ff >= p.F) continue;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int hh = h + kh - 1;
+        if (hh < 0 || hh >= p.H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ww = w + kw - 1;
+          if (ww < 0 || ww >= p.W) continue;
+          const long long nb = tok + ((long long)(kf - 1) * p.H + (kh - 1)) * p.W + (kw - 1);   // same sample: only f, h, w move
+          float xv[8];
+          aux_load8(p.x, nb * p.ld_x + c, p.fp16, xv);
+          const float* wrow = p.wt + (long long)((kf * 3 + kh) * 3 + kw) * p.C + c;
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(wrow)), w1 = __ldg(reinterpret_cast<const float4*>(wrow + 4));
+          acc[0] = fmaf(xv[0], w0.x, acc[0]); acc[1] = fmaf(xv[1], w0.y, acc[1]);
+          acc[2] = fmaf(xv[2], w0.z, acc[2]); acc[3] = fmaf(xv[3], w0.w, acc[3]);
+          acc[4] = fmaf(xv[4], w1.x, acc[4]); acc[5] = fmaf(xv[5], w1.y, acc[5]);
+          acc[6] = fmaf(xv[6], w1.z, acc[6]); acc[7] = fmaf(xv[7], w1.w, acc[7]);
+        }
+      }
+    }
+    aux_store8(p.out, tok * p.C + c, p.fp16, acc);
+  }
+}
+
 }  // namespace mhla

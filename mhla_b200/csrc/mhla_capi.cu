@@ -725,6 +725,26 @@ int mhla_gate_add(const mhla_gate_add_desc* d, void* stream_) {
   return MHLA_OK;
 }
 
+int mhla_dwconv3d(const mhla_dwconv3d_desc* d, void* stream_) {
+  if (!d || !d->x || !d->wt || !d->out) return MHLA_ERR_INVALID_ARGUMENT;
+  if (d->B < 1 || d->F < 1 || d->H < 1 || d->W < 1 || d->C < 8 || d->C % 8) return MHLA_ERR_UNSUPPORTED_SHAPE;
+  if (d->dtype != MHLA_BF16 && d->dtype != MHLA_FP16) return MHLA_ERR_INVALID_ARGUMENT;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(d->x) | reinterpret_cast<uintptr_t>(d->wt) |
+                       reinterpret_cast<uintptr_t>(d->bias) | reinterpret_cast<uintptr_t>(d->out);
+  if ((al & 15) != 0 || d->ld_x % 8 || d->ld_x < d->C) return MHLA_ERR_ALIGNMENT;
+  DeviceState* dst = nullptr;
+  int rc = device_state(&dst);
+  if (rc != MHLA_OK) return rc;
+  mhla::DwConv3dParams P{d->x, d->out, d->wt, d->bias, (long long)d->ld_x, d->B, d->F, d->H, d->W, d->C, d->dtype == MHLA_FP16};
+  const long long total = (long long)d->B * d->F * d->H * d->W * (d->C / 8);
+  const long long want = (total + 255) / 256, cap = (long long)dst->sms * 16;
+  const int grid = (int)(want < cap ? want : cap);
+  mhla::dwconv3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(P);
+  if (!cuda_ok(cudaGetLastError(), "dwconv3d_kernel")) return MHLA_ERR_CUDA;
+  g_last_launches = 1;
+  return MHLA_OK;
+}
+
 int mhla_bwd_prep(const mhla_bwd_prep_desc* d, void* stream_) {
   if (!d || !d->dout || !d->out || !d->den || !d->dnum || !d->dden) return MHLA_ERR_INVALID_ARGUMENT;
   if (d->rows < 1 || (d->D != 64 && d->D != 128)) return MHLA_ERR_UNSUPPORTED_SHAPE;

@@ -16,7 +16,7 @@ from einops import rearrange
 from torch import nn
 
 from ..mixing import BlockDistanceConv3D
-from ..ops import gate_add, mhla_blockmix, mhla_blockmix_grid, wan_prep
+from ..ops import dwconv3d_tokens, gate_add, mhla_blockmix, mhla_blockmix_grid, wan_prep
 
 
 class WanRMSNorm(nn.Module):
@@ -217,8 +217,14 @@ class _MHLAVideoBase(nn.Module):
         q, k, v = self.q(x), self.k(x), self.v(x)                                   # mhla_utils.py:279-288
         lepe = None
         if self.is_lepe:
-            lepe = self.lepe(rearrange(v, "b (f h w) c -> b c f h w", f=F_, h=H_, w=W_))
-            lepe = rearrange(lepe, "b c f h w -> b (f h w) c")
+            lepe_grad = torch.is_grad_enabled() and (v.requires_grad or self.lepe.weight.requires_grad)
+            if (self.fast_path and x.is_cuda and not lepe_grad and v.dtype in (torch.bfloat16, torch.float16) and C % 8 == 0
+                    and N == F_ * H_ * W_):
+                # the depthwise Conv3d straight on the token-major v (no NCDHW rearrangement, no cuDNN depthwise path)
+                lepe = dwconv3d_tokens(v, self.lepe.weight, self.lepe.bias, (F_, H_, W_))
+            else:
+                lepe = self.lepe(rearrange(v, "b (f h w) c -> b c f h w", f=F_, h=H_, w=W_))
+                lepe = rearrange(lepe, "b c f h w -> b (f h w) c")
         dtype = q.dtype
         W = self.block_attn.conv.weight
         training = torch.is_grad_enabled() and (q.requires_grad or v.requires_grad or W.requires_grad)

@@ -17,7 +17,7 @@ import torch
 
 from . import _capi
 
-__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "gated_rmsnorm", "gate_add", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
+__all__ = ["mhla", "mhla_blockmix", "mhla_blockmix_grid", "wan_prep", "gated_rmsnorm", "gate_add", "dwconv3d_tokens", "mhla_host", "mhla_causal", "naive_chunk_simple_mhla_fixed", "naive_recurrent_mhla",
            "last_launch_count"]
 
 _DT = {torch.bfloat16: _capi.MHLA_BF16, torch.float16: _capi.MHLA_FP16}
@@ -487,6 +487,31 @@ def gate_add(x: torch.Tensor, gate: Optional[torch.Tensor] = None, add: Optional
     d.out, d.ld_out = out.data_ptr(), Cc
     with torch.cuda.device(x.device):
         _capi.check(_capi.lib().mhla_gate_add(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_gate_add")
+    return out
+
+
+def dwconv3d_tokens(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], grid) -> torch.Tensor:
+    """Depthwise 3x3x3 convolution (zero padding 1) over the (F, H, W) token grid of a TOKEN-major tensor: x [B, F*H*W, C]
+    bf16 / fp16 -> [B, F*H*W, C] (``mhla_dwconv3d``, csrc/gated_norm_kernel.cuh).  ``weight`` / ``bias`` are the parameters
+    of the reference's ``self.lepe = nn.Conv3d(C, C, 3, padding=1, groups=C)`` ([C, 1, 3, 3, 3] / [C]): the result equals
+    ``rearrange(lepe(rearrange(x, "b (f h w) c -> b c f h w")), "b c f h w -> b (f h w) c")`` of mhla_utils.py:289-296
+    without the two rearrangements and cuDNN's depthwise path.  Inference only."""
+    _require_cuda(x, weight, bias)
+    B, N, Cc = x.shape
+    F_, H_, W_ = (int(v) for v in grid)
+    if x.dtype not in _DT or Cc % 8 or N != F_ * H_ * W_ or tuple(weight.shape) != (Cc, 1, 3, 3, 3):
+        raise ValueError("dwconv3d_tokens needs a bf16 / fp16 [B, F*H*W, C] tensor (C % 8 == 0) and a [C, 1, 3, 3, 3] weight")
+    x = x.detach()
+    if x.stride(-1) != 1 or x.stride(0) != N * x.stride(1):
+        x = x.contiguous()
+    wt = weight.detach().to(torch.float32).reshape(Cc, 27).t().contiguous()          # [27, C]
+    bf = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    out = torch.empty((B, N, Cc), dtype=x.dtype, device=x.device)
+    d = _capi.DwConv3dDesc()
+    d.B, d.F, d.H, d.W, d.C, d.dtype = B, F_, H_, W_, Cc, _DT[x.dtype]
+    d.x, d.ld_x, d.wt, d.bias, d.out = x.data_ptr(), x.stride(1), wt.data_ptr(), (bf.data_ptr() if bf is not None else None), out.data_ptr()
+    with torch.cuda.device(x.device):
+        _capi.check(_capi.lib().mhla_dwconv3d(C.byref(d), torch.cuda.current_stream().cuda_stream), "mhla_dwconv3d")
     return out
 
 

@@ -258,6 +258,25 @@ def test_gate_add_kernel(dtype, gated, added):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("dtype,bias,grid", [(torch.bfloat16, True, (3, 4, 5)), (torch.float16, False, (1, 6, 7)),
+                                             (torch.bfloat16, True, (5, 2, 1))])
+def test_dwconv3d_tokens_matches_conv3d(dtype, bias, grid):
+    """csrc/gated_norm_kernel.cuh dwconv3d_kernel (mhla_dwconv3d) against the reference's LePE path: nn.Conv3d(C, C, 3,
+    padding=1, groups=C) on the NCDHW rearrangement of v (mhla_utils.py:289-296), fp32 on CPU as the yardstick."""
+    import mhla_b200
+    torch.manual_seed(9)
+    B, C_ = 2, 64
+    F_, H_, W_ = grid
+    conv = torch.nn.Conv3d(C_, C_, 3, padding=1, groups=C_, bias=bias)
+    x = torch.randn(B, F_ * H_ * W_, C_).to(dtype)
+    with torch.no_grad():
+        ref = conv(x.float().view(B, F_, H_, W_, C_).permute(0, 4, 1, 2, 3)).permute(0, 2, 3, 4, 1).reshape(B, -1, C_)
+        y = mhla_b200.dwconv3d_tokens(x.cuda(), conv.weight.cuda(), None if conv.bias is None else conv.bias.cuda(), grid)
+    tol = 4e-3 if dtype == torch.bfloat16 else 6e-4
+    assert oracle.err_ratio(ref, y.float().cpu()) < tol
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("normalize_out,gated,lepe,post", [(False, False, False, True), (True, True, False, True),
                                                            (True, False, True, True), (False, True, True, True),
                                                            (False, True, True, "epilogue"), (True, True, False, "epilogue"),

@@ -91,6 +91,19 @@ with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
     m.fuse_post = False
     t_u = timed(lambda: m(x, sl, gs, freqs))
     y2 = m(x, sl, gs, freqs)
+    m.fuse_post = True
+    m.fast_path = False
+    t_ref = timed(lambda: m(x, sl, gs, freqs))
+    y3 = m(x, sl, gs, freqs)
+    m.fast_path = True
+    # the LePE convolution alone: token-major depthwise kernel vs the reference's NCDHW rearrangement + cuDNN depthwise Conv3d
+    vv = torch.randn(1, N, dim, device="cuda").bfloat16()
+    t_dw = timed_graph(lambda: mhla_b200.dwconv3d_tokens(vv, m.lepe.weight, m.lepe.bias, grid))
+    from einops import rearrange as _re
+    t_cudnn = timed(lambda: _re(m.lepe(_re(vv, "b (f h w) c -> b c f h w", f=grid[0], h=grid[1], w=grid[2])), "b c f h w -> b (f h w) c"))
+print(f"B=1 gated + lepe layer: fused path {t_f:.0f} us vs reference-style path {t_ref:.0f} us ({t_ref / t_f:.2f}x), rel diff "
+      f"{float((y1.float() - y3.float()).norm() / y3.float().norm()):.2e}; LePE conv alone: token-major kernel {t_dw:.0f} us vs "
+      f"rearrange + cuDNN depthwise Conv3d {t_cudnn:.0f} us")
 print(f"B=1 gated + lepe layer: one gate_add launch {t_f:.0f} us vs torch elementwise passes {t_u:.0f} us, rel diff "
       f"{float((y1.float() - y2.float()).norm() / y2.float().norm()):.2e}")
 
