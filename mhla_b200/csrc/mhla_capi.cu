@@ -736,7 +736,7 @@ int mhla_dwconv3d(const mhla_dwconv3d_desc* d, void* stream_) {
   int rc = device_state(&dst);
   if (rc != MHLA_OK) return rc;
   mhla::DwConv3dParams P{d->x, d->out, d->wt, d->bias, (long long)d->ld_x, d->B, d->F, d->H, d->W, d->C, d->dtype == MHLA_FP16};
-  const long long total = (long long)d->B * d->F * d->H * d->W * (d->C / 8);
+  const long long total = (long long)d->B * d->F * d->H * ((d->W + mhla::kDwTile - 1) / mhla::kDwTile) * (d->C / 8);
   const long long want = (total + 255) / 256, cap = (long long)dst->sms * 16;
   const int grid = (int)(want < cap ? want : cap);
   mhla::dwconv3d_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream_)>>>(P);
