@@ -223,6 +223,81 @@ class BlockmixGridFunction(torch.autograd.Function):
         return dq.to(q.dtype), dk.to(k.dtype), dv.to(v.dtype), dW, None, None, None
 
 
+# ------------------------------------------------------------------------------------------------ Wan pre-processing
+def wan_prep_reference(x, w, cos, sin, head_dim: int, eps_norm: float = 1e-6, eps: float = 1e-6):
+    """Differentiable torch restatement of what ``ops.wan_prep`` computes for ONE of its two inputs (mhla_utils.py:267-276,
+    :127-156): y = relu(x * rsqrt(mean_C(x^2) + eps_norm) * w) + eps, then the interleaved-pair rotation of every head by
+    the token's angles.  x [B, N, C], w [C] or None, cos / sin [N, D/2] -> [B, N, C // D, D] in x's float type.  The
+    checker of ``wan_prep_backward`` (tests/test_autograd_cpu.py) and the formula the CUDA kernel is tested against."""
+    B, N, Cc = x.shape
+    D = int(head_dim)
+    r = torch.rsqrt(x.pow(2).mean(dim=-1, keepdim=True) + eps_norm)
+    y = x * r
+    if w is not None:
+        y = y * w
+    y = torch.relu(y) + eps
+    yp = y.reshape(B, N, Cc // D, D // 2, 2)
+    a, b = yp[..., 0], yp[..., 1]
+    c, s_ = cos[None, :, None, :].to(y.dtype), sin[None, :, None, :].to(y.dtype)
+    return torch.stack((a * c - b * s_, a * s_ + b * c), dim=-1).reshape(B, N, Cc // D, D)
+
+
+def wan_prep_backward(x, w, cos, sin, head_dim: int, eps_norm: float, g_rope, g_plain=None):
+    """Gradients of ``wan_prep_reference`` w.r.t. x and w given the gradient of the roped output (and, optionally, of the
+    un-roped output relu(.) + eps): returns (gx [B, N, C], gw [C] or None) in fp32 (fp64 for fp64 inputs).
+      rotation^T:  g_a = g0 c + g1 s,  g_b = -g0 s + g1 c
+      relu:        g_y = g * [y > 0]
+      RMSNorm:     u = x r, y = u w:  gw = sum_rows g_y u,  gx = r (g_u - u mean_C(g_u u)),  g_u = g_y w"""
+    f = torch.float64 if x.dtype == torch.float64 else torch.float32
+    B, N, Cc = x.shape
+    D = int(head_dim)
+    xf = x.to(f)
+    r = torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + eps_norm)
+    u = xf * r
+    wf = None if w is None else w.to(f)
+    y = u if wf is None else u * wf
+    g = g_rope.to(f).reshape(B, N, Cc // D, D // 2, 2)
+    g0, g1 = g[..., 0], g[..., 1]
+    c, s_ = cos[None, :, None, :].to(f), sin[None, :, None, :].to(f)
+    gy = torch.stack((g0 * c + g1 * s_, g1 * c - g0 * s_), dim=-1).reshape(B, N, Cc)
+    if g_plain is not None:
+        gy = gy + g_plain.to(f).reshape(B, N, Cc)
+    gy = gy * (y > 0).to(f)
+    gw = None if wf is None else (gy * u).sum(dim=(0, 1))
+    gu = gy if wf is None else gy * wf
+    gx = r * (gu - u * (gu * u).mean(dim=-1, keepdim=True))
+    return gx, gw
+
+
+class WanPrepFunction(torch.autograd.Function):
+    """Training through the fused Wan pre-processing: forward = the ONE CUDA launch of ``ops.wan_prep`` (RMSNorm over C,
+    relu + eps, RoPE, 16-bit token-major outputs), backward = ``wan_prep_backward`` (a dozen fp32 elementwise / row
+    reductions per input) - instead of autograd through ~10 fp32 / complex temporaries per input in both directions
+    (mhla_utils.py:267-276, :127-156, :303-316).  Returns (q_rope, k_rope) as [B, N, heads, D]."""
+
+    @staticmethod
+    def forward(ctx, xq, xk, wq, wk, cos, sin, head_dim, eps_norm, eps):
+        from . import ops
+        qr, kr, _, _ = ops.wan_prep(xq, xk, wq, wk, cos, sin, head_dim, eps_norm=eps_norm, eps=eps, want_plain=False)
+        ctx.save_for_backward(xq, xk, wq, wk, cos, sin)
+        ctx.head_dim, ctx.eps_norm = int(head_dim), float(eps_norm)
+        return qr, kr
+
+    @staticmethod
+    def backward(ctx, gq, gk):
+        xq, xk, wq, wk, cos, sin = ctx.saved_tensors
+        gxq = gxk = gwq = gwk = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[2]:
+            gxq, gwq = wan_prep_backward(xq, wq, cos, sin, ctx.head_dim, ctx.eps_norm, gq)
+            gxq = gxq.to(xq.dtype)
+            gwq = None if (gwq is None or not ctx.needs_input_grad[2]) else gwq.to(wq.dtype)
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[3]:
+            gxk, gwk = wan_prep_backward(xk, wk, cos, sin, ctx.head_dim, ctx.eps_norm, gk)
+            gxk = gxk.to(xk.dtype)
+            gwk = None if (gwk is None or not ctx.needs_input_grad[3]) else gwk.to(wk.dtype)
+        return gxq, gxk, gwq, gwk, None, None, None, None, None
+
+
 # ------------------------------------------------------------------------------------------------ variant C
 def causal_backward(q, k, v, mm, do, chunk_size: int = 64, scale: Optional[float] = None):
     """Gradients of o = causal_chunk(q, k, v, mm) (naive.py:10-83): q,k [B,T,H,K], v,do [B,T,H,V], mm [L,L].

@@ -116,6 +116,8 @@ class _MHLAVideoBase(nn.Module):
         # measured slower than the streaming pass on a B200 - the epilogue's row-wise global loads queue behind the TMA
         # stream, profiles/r02c_notes.md); False: plain torch ops
         self.fuse_post = kwargs.get("fuse_post", True)
+        # extension: training goes through the fused pre-processing launch with an analytic backward (autograd.WanPrepFunction)
+        self.train_fused_prep = kwargs.get("train_fused_prep", True)
         self.is_lepe = lepe
         self.norm_q = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
         self.norm_k = WanRMSNorm(dim, eps=eps) if qk_norm else nn.Identity()
@@ -232,6 +234,21 @@ class _MHLAVideoBase(nn.Module):
                   and -(-p1 // max(1, min(p1, 128 // (p2 * p3)))) <= 2)   # the kernel's 3-D block view applies
         if view3d and not training:
             return self._forward_fused(x, q, k, v, lepe, (F_, H_, W_), grid_sizes, freqs)
+        norms_ok = all(isinstance(n_, (WanRMSNorm, nn.Identity)) for n_ in (self.norm_q, self.norm_k))
+        if view3d and training and not self.normalize_out and self.train_fused_prep and norms_ok:
+            # training in the shipped configuration (norm_output: false) without a layout copy AND without autograd through
+            # the fp32 / complex pre-processing: the forward is the fused pre-processing launch, its backward is analytic
+            # (autograd.WanPrepFunction); the operator trains through the 3-D block view (autograd.BlockmixGridFunction)
+            from ..autograd import WanPrepFunction
+            cos, sin = _rope_tables((F_, H_, W_), freqs, x.device)
+            wq = self.norm_q.weight if isinstance(self.norm_q, WanRMSNorm) else None
+            wk = self.norm_k.weight if isinstance(self.norm_k, WanRMSNorm) else None
+            eps_n = self.norm_q.eps if isinstance(self.norm_q, WanRMSNorm) else 1e-6
+            q_rope, k_rope = WanPrepFunction.apply(q, k, wq, wk, cos, sin, D, eps_n, self.eps)
+            v4 = (v if v.dtype == q_rope.dtype else v.to(q_rope.dtype)).view(B, N, nh, D)
+            out = mhla_blockmix_grid(q_rope, k_rope, v4, W, (F_, H_, W_), self.blocks_layout, eps=self.eps,
+                                     normalize=False).to(dtype)
+            return self._post(x, out, lepe, B, N, C, fuse_norm=False)
         q = torch.relu(self.norm_q(q.float())) + self.eps                          # :308, 267-276
         k = torch.relu(self.norm_k(k.float())) + self.eps
         q, k, v = (t.view(B, N, nh, D) for t in (q, k, v))
@@ -256,6 +273,10 @@ class _MHLAVideoBase(nn.Module):
             out = mhla_blockmix(blk(q_rope), blk(k_rope), blk(v), W, eps=self.eps, normalize=False, **fuse)
         if out.dim() == 5:
             out = rearrange(out, "b h (fb hb wb) (p1 p2 p3) d -> b (fb p1 hb p2 wb p3) h d", **kw).to(dtype)   # :343-356
+        return self._post(x, out, lepe, B, N, C, fuse_norm)
+
+    def _post(self, x, out, lepe, B, N, C, fuse_norm):
+        """Everything between the operator and the layer's output (mhla_utils.py:357-366), plain torch (differentiable)."""
         if self._gnorm == "head" and not fuse_norm:
             out = self.g_norm(out)                                                  # :360-364 per-head RMSNorm
         out = out.reshape(B, N, C)

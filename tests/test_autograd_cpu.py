@@ -115,3 +115,52 @@ def test_causal_backward_native_composition(monkeypatch, T, K, V):
     got = autograd.causal_backward_native(q.detach(), k.detach(), v.detach(), mm.detach(), do)
     for r, o in zip(ref, got):
         assert oracle.err_ratio(r, o.double()) < 1e-6
+
+
+@pytest.mark.parametrize("with_weight,with_plain", [(True, False), (False, False), (True, True)])
+def test_wan_prep_backward_matches_autograd(with_weight, with_plain):
+    """autograd.wan_prep_backward (the backward of WanPrepFunction: rotation^T, relu mask, RMSNorm over the full channel
+    dim) against torch.autograd of the differentiable restatement of the pre-processing (mhla_utils.py:267-276, :127-156),
+    float64.  The restatement itself is checked against the reference's RoPE in test_modules (rope_apply) and the CUDA
+    kernel against the reference pre-processing in test_wan_prep_kernel_matches_reference_preprocessing."""
+    from mhla_b200.autograd import wan_prep_backward, wan_prep_reference
+    torch.manual_seed(11)
+    B, N, H, D = 2, 12, 3, 8
+    x = torch.randn(B, N, H * D, dtype=torch.float64, requires_grad=True)
+    w = (torch.rand(H * D, dtype=torch.float64) + 0.5).requires_grad_(True) if with_weight else None
+    ang = torch.rand(N, D // 2, dtype=torch.float64) * 6.28
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    y = wan_prep_reference(x, w, cos, sin, D, eps_norm=1e-5, eps=1e-6)
+    g = torch.randn_like(y)
+    loss = (y * g).sum()
+    gp = None
+    if with_plain:   # the un-roped output relu(.) + eps gets a gradient of its own (normaliser operands)
+        r = torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-5)
+        plain = torch.relu(x * r * w) + 1e-6
+        gp = torch.randn_like(plain)
+        loss = loss + (plain * gp).sum()
+    grads = torch.autograd.grad(loss, [x] + ([w] if with_weight else []))
+    gx, gw = wan_prep_backward(x.detach(), None if w is None else w.detach(), cos, sin, D, 1e-5, g, gp)
+    assert torch.allclose(gx, grads[0], rtol=1e-9, atol=1e-11)
+    if with_weight:
+        assert torch.allclose(gw, grads[1], rtol=1e-9, atol=1e-11)
+    else:
+        assert gw is None
+
+
+def test_wan_prep_reference_is_the_modules_preprocessing():
+    """wan_prep_reference == relu(WanRMSNorm(x)) + eps followed by the module's rope_apply (the reference-style path of
+    modules/wan.py, itself checked against the reference's complex RoPE)."""
+    from mhla_b200.autograd import wan_prep_reference
+    from mhla_b200.modules.wan import WanRMSNorm, rope_apply, _rope_tables
+    torch.manual_seed(12)
+    grid, H, D = (2, 3, 4), 2, 12
+    N = grid[0] * grid[1] * grid[2]
+    x = torch.randn(2, N, H * D)
+    norm = WanRMSNorm(H * D, eps=1e-5)
+    norm.weight.data = torch.rand(H * D) + 0.5
+    freqs = oracle.rope_freqs_wan(D)
+    ref = rope_apply((torch.relu(norm(x)) + 1e-6).view(2, N, H, D), torch.tensor([list(grid)] * 2), freqs)
+    cos, sin = _rope_tables(grid, freqs, x.device)
+    got = wan_prep_reference(x, norm.weight.detach(), cos, sin, D, eps_norm=1e-5, eps=1e-6)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)

@@ -313,15 +313,21 @@ def test_wan_module_training_step_through_the_3d_block_view():
     x = torch.randn(2, N, dim, device="cuda")
     gs = torch.tensor([list(grid)] * 2, dtype=torch.long)
     freqs = oracle.rope_freqs_wan(dim // heads)
+    m.norm_q.weight.data.add_(0.2 * torch.rand_like(m.norm_q.weight))
+    m.norm_k.weight.data.add_(0.2 * torch.rand_like(m.norm_k.weight))
     grads = []
-    for fast in (True, False):
-        m.fast_path = fast
+    # (fast, fused pre-processing): 3-D view + autograd.WanPrepFunction (default) | 3-D view + torch pre-processing |
+    # block-major copies + torch pre-processing (reference-style)
+    for fast, prep in ((True, True), (True, False), (False, False)):
+        m.fast_path, m.train_fused_prep = fast, prep
         m.zero_grad()
         with torch.autocast("cuda", dtype=torch.bfloat16):
             y = m(x, torch.tensor([N, N]), gs, freqs)
         y.float().square().mean().backward()
         grads.append([p.grad.detach().float().cpu().clone() for p in (m.q.weight, m.k.weight, m.v.weight,
-                                                                       m.block_attn.conv.weight)])
-    for a, b in zip(*grads):
-        assert float(b.abs().max()) > 0
-        assert oracle.err_ratio(b, a) < 2e-2
+                                                                       m.block_attn.conv.weight, m.norm_q.weight,
+                                                                       m.norm_k.weight)])
+    for g_ in grads[:2]:
+        for a, b in zip(g_, grads[2]):
+            assert float(b.abs().max()) > 0
+            assert oracle.err_ratio(b, a) < 2e-2

@@ -119,11 +119,14 @@ def train_step():
     y.float().square().mean().backward()
 
 
-m.fast_path = True
+m.fast_path, m.train_fused_prep = True, True
+t_p = timed(train_step, reps=5)
+m.fast_path, m.train_fused_prep = True, False
 t_g = timed(train_step, reps=5)
 m.fast_path = False
 t_b = timed(train_step, reps=5)
-print(f"B=1 training step of the layer: 3-D block view {t_g:.0f} us vs block-major copies {t_b:.0f} us")
+print(f"B=1 training step of the layer: 3-D block view + fused pre-processing with analytic backward {t_p:.0f} us, 3-D block "
+      f"view + torch pre-processing {t_g:.0f} us, block-major copies (reference-style) {t_b:.0f} us")
 
 # the fused gate / "+ lepe" epilogue at OPERATOR level (the layer numbers above are dominated by the depthwise Conv3d):
 # one launch with out_gate / out_add against the plain launch followed by the eager elementwise passes
