@@ -85,6 +85,42 @@ def test_invalid_arguments_are_rejected_before_any_cuda_call():
     assert L.mhla_causal_workspace_bytes(C.byref(c)) == 0
 
 
+def test_streaming_entry_points_validate_their_descriptors():
+    """mhla_gate_add / mhla_dwconv3d / mhla_gated_rmsnorm reject bad descriptors before touching CUDA (status codes of
+    include/mhla_b200.h: -1 invalid argument, -2 unsupported shape, -3 alignment)."""
+    L = _capi.lib()
+    g = _capi.GateAddDesc()
+    g.rows, g.C, g.dtype = 16, 64, 0
+    assert L.mhla_gate_add(C.byref(g), None) == -1                # x / out NULL
+    g.x, g.out, g.ld_x, g.ld_out = 0x1000, 0x2000, 64, 64
+    g.C = 60
+    assert L.mhla_gate_add(C.byref(g), None) == -2                # C % 8
+    g.C, g.x = 64, 0x1004
+    assert L.mhla_gate_add(C.byref(g), None) == -3                # 16-byte alignment
+    g.x, g.ld_x = 0x1000, 32
+    assert L.mhla_gate_add(C.byref(g), None) == -3                # pitch shorter than a row
+    g.ld_x, g.dtype = 64, 7
+    assert L.mhla_gate_add(C.byref(g), None) == -1                # dtype
+
+    d = _capi.DwConv3dDesc()
+    d.B, d.F, d.H, d.W, d.C, d.dtype = 1, 3, 4, 5, 64, 0
+    assert L.mhla_dwconv3d(C.byref(d), None) == -1                # NULL tensors
+    d.x, d.wt, d.out, d.ld_x = 0x1000, 0x2000, 0x3000, 64
+    d.C = 12
+    assert L.mhla_dwconv3d(C.byref(d), None) == -2                # C % 8
+    d.C, d.F = 64, 0
+    assert L.mhla_dwconv3d(C.byref(d), None) == -2                # empty grid
+    d.F, d.ld_x = 3, 60
+    assert L.mhla_dwconv3d(C.byref(d), None) == -3                # pitch
+
+    n = _capi.GatedNormDesc()
+    n.rows, n.D, n.dtype = 8, 256, 0
+    assert L.mhla_gated_rmsnorm(C.byref(n), None) == -1
+    n.x, n.out, n.ld_x = 0x1000, 0x2000, 256
+    n.D = 96
+    assert L.mhla_gated_rmsnorm(C.byref(n), None) == -2           # D not in {64, 128, 256}
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_capi, "_lib", None)
     monkeypatch.setattr(_capi, "LIB_PATH", str(tmp_path / "nope.so"))
