@@ -98,7 +98,7 @@ class _MHLAImage(nn.Module):
             obuf = torch.empty((B, M, w, H, D), dtype=cdtype, device=x.device)
             # "+ lepe" (mhla.py:271-273): short sequences (the whole unit on chip, csrc/smalln_kernel.cuh) add it in the
             # readout epilogue, in fp32 before the single rounding; above that size the general kernel's epilogue has no
-            # latency budget for a second input stream (DESIGN.md 3.6) and ONE streaming launch behind the operator adds it
+            # latency budget for a second input stream (DESIGN.md 3.5) and ONE streaming launch behind the operator adds it
             small = D == 64 and M <= 64 and M * w <= 256
             add = lepe.reshape(B, M, w, H, D).permute(0, 3, 1, 2, 4) if (self.fuse_lepe and small) else None
             mhla_blockmix(q5, k5, v5, W, eps=self.eps, normalize=True, out=obuf.permute(0, 3, 1, 2, 4), out_add=add)   # mhla.py:262-268
